@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — kNN queries/s on the north-star workload (BASELINE.json):
+knn_predict on an 811,457 x 512 bank, k=200, t=0.1, 9 classes.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode bf16|tf32x3|exact]
+  python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+
+A step = one knn_predict call over one batch of Q synthetic queries.
+  value : queries/s with queries, bank (prepared, cached) and labels resident in HBM
+  e2e   : the same through the public API with HOST (pinned) queries: H2D copy of the batch,
+          knn_predict, D2H of the predicted class column, all inside the timed region
+  N > 1 : the bank is row-sharded over the ranks (north-star mode 4); every rank holds the
+          whole query batch; one all-gather of (Q,k) candidate keys + merge per step.
+          Fixed total work as N grows -> "scaling": "strong".
+One JSON line on rank 0 (contract in the task statement).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "self-supervised-wafermaps_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+N_BANK, DIM, KNN_K, KNN_T, N_CLASSES = 811457, 512, 200, 0.1, 9
+WAVE = 148 * 128  # queries one resident wave of CTAs covers
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops_sustained"], bf16_burst=p["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, src="fallback")
+
+
+def make_inputs(device, n_bank, n_query, dim, seed):
+    """clustered synthetic embeddings generated on the device under test, in chunks of 65,536
+    rows so results do not depend on the total size."""
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    prior = torch.tensor([859, 111, 1037, 1936, 719, 30, 173, 239, 7345], dtype=torch.float64, device=device)
+    cent = torch.nn.functional.normalize(torch.randn(N_CLASSES, dim, generator=g, device=device), dim=1)
+
+    def rows(n):
+        out = torch.empty(n, dim, device=device)
+        lab = torch.empty(n, dtype=torch.int64, device=device)
+        for lo in range(0, n, 65536):
+            hi = min(n, lo + 65536)
+            l = torch.multinomial(prior, hi - lo, replacement=True, generator=g)
+            x = cent[l] + 1.4 * torch.randn(hi - lo, dim, generator=g, device=device) / dim ** 0.5
+            out[lo:hi] = torch.nn.functional.normalize(x, dim=1)
+            lab[lo:hi] = l
+        return out, lab
+
+    bank_nd, labels = rows(n_bank)
+    q, _ = rows(n_query)
+    return bank_nd, labels, q
+
+
+class ClockSampler:
+    def __init__(self, index=0):
+        self.rows, self.stop = [], threading.Event()
+        self.index = index
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_rate(batch, n_calls, threads=None):
+    """The reference algorithm (oracle R32: lightly's knn_predict restated op for op) on torch
+    CPU fp32 with all host threads, on a bounded sample of the SAME workload: `n_calls` calls
+    of `batch` queries against the full 811,457 x 512 bank (after one untimed warm-up call)."""
+    import torch
+
+    from oracle import knn_oracle as O
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(811)
+    bank = torch.nn.functional.normalize(torch.randn(N_BANK, DIM, generator=g), dim=1).t().contiguous()
+    labels = torch.randint(0, N_CLASSES, (N_BANK,), generator=g)
+    q = torch.nn.functional.normalize(torch.randn(batch, DIM, generator=g), dim=1)
+    O.knn_predict_r32(q, bank, labels, N_CLASSES, KNN_K, KNN_T)
+    times = []
+    for _ in range(n_calls):
+        t0 = time.perf_counter()
+        O.knn_predict_r32(q, bank, labels, N_CLASSES, KNN_K, KNN_T)
+        times.append(time.perf_counter() - t0)
+    return batch * n_calls / sum(times), times, threads
+
+
+def cpu_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 1024
+    rate, times, threads = cpu_reference_rate(batch, args.warmup + args.steps)
+    times = times[args.warmup:]
+    rate = batch * len(times) / sum(times)
+    sample = f"{len(times)} calls of B={batch} queries against the full {N_BANK}x{DIM} bank, k={KNN_K}"
+    line = {
+        "impl": "reference", "metric": "kNN queries/s @811k×512 bank, k=200", "value": rate, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"knn_predict N={N_BANK} D={DIM} k={KNN_K} t={KNN_T} C={N_CLASSES}; B={batch} per step",
+                   "reference": "lightly knn_predict restated (oracle R32), torch CPU fp32 (MKL), all host threads",
+                   "cpu": cpu_name()},
+        "cpu_baseline": {"value": rate, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mode", default=os.environ.get("B200KNN_BENCH_MODE", "bf16"))
+    ap.add_argument("--queries", type=int, default=4 * WAVE, help="queries per step (default 75,776 = 4 waves)")
+    ap.add_argument("--bank", type=int, default=N_BANK)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import b200knn
+    from b200knn import knn as K
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Q, N, mode = args.queries, args.bank, args.mode
+    b200knn.set_default_mode(mode)
+
+    bank_nd, labels, q = make_inputs(dev, N, Q, DIM, seed=811)
+    if world > 1:
+        lo, hi = b200knn.shard_bounds(N, world, rank)
+        shard = bank_nd[lo:hi].t().contiguous()  # this rank's (D, rows) slice, reference layout
+        del bank_nd
+        sb = b200knn.ShardedBank(shard, labels, N, mode=mode)
+        bank = shard
+        n_local = hi - lo
+
+        def predict(qd):
+            return sb.knn_predict(qd, N_CLASSES, KNN_K, KNN_T)
+    else:
+        bank = bank_nd.t().contiguous()  # (D,N) contiguous as knn.py:80 builds it
+        del bank_nd
+        n_local = N
+
+        def predict(qd):
+            return b200knn.knn_predict(qd, bank, labels, N_CLASSES, KNN_K, KNN_T)
+
+    # bank preparation (cached per bank tensor; once per validation epoch in the reference) — timed apart
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if mode != "exact":
+        K.bank_cache.get(bank, mode)
+    e1.record()
+    torch.cuda.synchronize()
+    prepare_ms = e0.elapsed_time(e1)
+
+    q_host = q.cpu().pin_memory()
+    top1_host = torch.empty(Q, dtype=torch.int64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        return predict(q)
+
+    def step_e2e():
+        qd = q_host.to(dev, non_blocking=True)
+        pred = predict(qd)
+        top1_host.copy_(pred[:, 0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    K.profile_events = []
+    with ClockSampler(local) as clocks:
+        total_ms = timed(step_resident, args.steps)
+    events = K.profile_events
+    K.profile_events = None
+    kern_ms = [a.elapsed_time(b) for a, b in events]
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        pk = peaks()
+        ms_per_step = total_ms / args.steps
+        value = Q / (ms_per_step * 1e-3)
+        kern = sum(kern_ms) / max(1, len(kern_ms))
+        flops = 2.0 * Q * n_local * DIM  # algorithmic: 2*N*D per query, this rank's rows
+        achieved = flops / (kern * 1e-3) / 1e12
+        plan = b200knn.plan_info(Q, n_local, DIM, KNN_K, mode)
+        if mode == "bf16":
+            roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["bf16"], "traffic": None,
+                    "kernel": "tc_topk_kernel<BF16,256> (+ split-merge when splits>1)",
+                    "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_ms": kern}
+        elif mode == "tf32x3":
+            roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"] / 2, "unit": "TFLOP/s",
+                    "frac": achieved / (pk["bf16"] / 2), "executed_frac": 3 * achieved / (pk["bf16"] / 2),
+                    "traffic": None, "kernel": "tc_topk_kernel<TF32X3,128>",
+                    "peak_source": f"{pk['src']} bf16 sustained / 2 (tf32 runs at half the bf16 rate)",
+                    "kernel_ms": kern}
+        else:
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            roof = {"bound": "fp32-cuda-core", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp32_peak, "traffic": None, "kernel": "exact_topk_kernel",
+                    "peak_source": "nominal 148 SM x 128 FMA/clk x 1.965 GHz", "kernel_ms": kern}
+        launches_per_step = (0 if mode == "exact" else 1) + 1 + (1 if plan["splits"] > 1 else 0) + 1 \
+            + (1 if world > 1 else 0)
+        line = {
+            "metric": "kNN queries/s @811k×512 bank, k=200", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "exact": "f32"}[mode], "data": "synthetic",
+            "config": {"workload": f"knn_predict N={N} D={DIM} k={KNN_K} t={KNN_T} C={N_CLASSES}; "
+                                   f"Q={Q} queries per step (clustered synthetic, WM-811K class priors)",
+                       "mode": mode, "bank_sharding": f"row-sharded over {world} GPU(s)" if world > 1 else "none",
+                       "l2": "inputs larger than L2 (prepared bank %.0f MB)" % (n_local * DIM * (2 if mode == "bf16" else 8 if mode == "tf32x3" else 4) / 1e6),
+                       "plan": plan, "bank_prepare_ms_excluded": prepare_ms},
+            "roofline": roof,
+            "e2e": {"value": Q / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": Q * DIM * 4, "d2h_bytes_per_step": Q * 8,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, times, threads = cpu_reference_rate(256, 8)
+            line["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": threads, "kind": "port",
+                                    "cpu": cpu_name(),
+                                    "sample": f"8 calls of B=256 queries against the full {N_BANK}x{DIM} bank "
+                                              f"(oracle R32 = lightly knn_predict restated, torch CPU fp32)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

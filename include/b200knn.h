@@ -1,0 +1,151 @@
+/*
+ * b200knn.h — C ABI of libb200knn.so: the B200 (sm_100a) kNN hot path.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * faris-k/self-supervised-wafermaps:  lightly's
+ *     knn_predict(feature, feature_bank, feature_labels, num_classes, knn_k, knn_t)
+ * bound at   src/ssl_wafermap/models/knn.py:16   and called at
+ *            src/ssl_wafermap/models/knn.py:91-98 and :205-212,
+ * plus the brute-force neighbour retrieval of
+ *            notebooks/2.0-Figures-nearest-neighbors.ipynb:54.
+ * The reference is pure Python over ATen ops (mm -> topk -> gather -> exp ->
+ * scatter -> sum -> argsort); there is no FFI in the reference, so these entry
+ * points are what a ctypes binding for that path binds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says `host_`;
+ *   - the caller owns every buffer, including workspaces (the library never
+ *     allocates or frees device memory);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no
+ *     implicit synchronisation, no default-stream use;
+ *   - return code 0 = ok; otherwise a negative B200KNN_E_* code and
+ *     b200knn_last_error() returns a thread-local message;
+ *   - no C++ exception crosses this boundary; the library never calls
+ *     exit/abort.
+ */
+#ifndef B200KNN_H_
+#define B200KNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200KNN_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define B200KNN_OK 0
+#define B200KNN_E_ARG (-1)       /* bad argument (shape, k > N, alignment ...) */
+#define B200KNN_E_CUDA (-2)      /* a CUDA runtime/driver call failed */
+#define B200KNN_E_WORKSPACE (-3) /* workspace too small */
+#define B200KNN_E_UNSUPPORTED (-4)
+
+/* element types of caller tensors */
+#define B200KNN_F32 0
+#define B200KNN_F16 1
+#define B200KNN_BF16 2
+
+/* layouts of a 2-D (rows = vectors) operand as the caller holds it */
+#define B200KNN_LAYOUT_DN 0 /* (D,N) contiguous, vectors are COLUMNS: knn.py:80 `.t().contiguous()` */
+#define B200KNN_LAYOUT_ND 1 /* (N,D) contiguous, vectors are rows: queries, notebook banks */
+
+/* similarity-contraction modes */
+#define B200KNN_MODE_EXACT 0 /* CUDA-core fp32, sim = sequential fmaf over d (the on-device golden) */
+#define B200KNN_MODE_BF16 1  /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulate */
+#define B200KNN_MODE_TF32X3 2 /* tcgen05 kind::tf32, hi/lo split operands, 3 MMAs per k-step */
+
+int b200knn_version(void);
+const char* b200knn_last_error(void);
+
+/*
+ * Operand preparation (replaces nothing in the reference; it is the cached,
+ * one-off relayout of the bank that knn.py:80 produces and of the queries of
+ * knn.py:90).  Converts `src` (element type src_dtype, layout src_layout,
+ * n_vec vectors of dimension dim, leading dimension ld in ELEMENTS) into the
+ * K-major row layout the tensor-core kernels stream with TMA:
+ *   mode BF16  : dst_hi = (n_vec, dim) bf16 (round-to-nearest-even); dst_lo unused
+ *   mode TF32X3: dst_hi = (n_vec, dim) f32 holding tf32-truncated values,
+ *                dst_lo = (n_vec, dim) f32 holding  x - hi  (exact)
+ */
+int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout,
+                         int64_t n_vec, int dim, int64_t ld, int mode,
+                         void* dst_hi, void* dst_lo, void* stream);
+
+/*
+ * Fused similarity + streaming top-k   (replaces torch.mm + Tensor.topk,
+ * a1.1/a1.2 of SURVEY.md §8; lightly knn_predict lines 1-2).
+ *
+ *   mode EXACT : q = (B,dim) caller tensor (q_dtype, row-major, ld = q_ld);
+ *                bank = caller tensor (bank_dtype, bank_layout, ld = bank_ld)
+ *   mode BF16 / TF32X3 : q_hi/q_lo and bank_hi/bank_lo are b200knn_prepare_rows
+ *                outputs (K-major rows); q_dtype/bank_dtype/layout args ignored.
+ *
+ * Output: out_keys = (B, k) uint64 selection keys sorted
+ * descending under the canonical total order (sim desc, index asc):
+ *     key = orderable_u32(sim) << 32 | (0xFFFFFFFF - (idx + idx_offset))
+ * Decode with b200knn_decode_keys.  `idx_offset` is added to every bank row
+ * index (bank row-sharding across GPUs).
+ * workspace: at least b200knn_topk_workspace_bytes(...) bytes, 256-byte aligned.
+ */
+size_t b200knn_topk_workspace_bytes(int64_t B, int64_t N, int dim, int k, int mode);
+
+int b200knn_topk(int mode,
+                 const void* q_hi, const void* q_lo, int q_dtype, int64_t q_ld,
+                 const void* bank_hi, const void* bank_lo, int bank_dtype,
+                 int bank_layout, int64_t bank_ld,
+                 int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
+                 uint64_t* out_keys,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Merge G sorted candidate lists per query into one (replaces nothing in the
+ * reference; it is the exchange step of the bank-row-sharded mode, applied to
+ * the buffer an all-gather of per-shard b200knn_topk outputs produces).
+ *   keys_in : (G, B, k_in) uint64, each (g,b,:) sorted descending
+ *   keys_out: (B, k_out) uint64 sorted descending, k_out <= G*k_in
+ */
+int b200knn_merge(const uint64_t* keys_in, int G, int64_t B, int k_in, int k_out,
+                  uint64_t* keys_out, void* stream);
+
+/* keys (B,k) -> sims (B,k) f32 and idx (B,k) int64  (Tensor.topk's two outputs).
+ * Empty slots (fewer than k finite candidates) decode to sim=-inf, idx=-1. */
+int b200knn_decode_keys(const uint64_t* keys, int64_t n_keys, float* sims,
+                        int64_t* idx, void* stream);
+
+/*
+ * Weighted class vote + ranking  (replaces gather / div+exp / zeros+scatter /
+ * mul+sum / argsort, a1.3-a1.7 of SURVEY.md §8; lightly knn_predict lines 3-7).
+ *   keys   : (B,k) selection keys (sorted descending)
+ *   labels : (N,) int64 class ids of the bank rows, indexed by (idx - label_offset)
+ *   pred   : (B,C) int64 classes ordered by (score desc, class asc)
+ *   scores : optional (B,C) f64 class scores (may be NULL)
+ *   err_flag: device int32, set to 1 if any label is outside [0,C) — the
+ *             reference raises from scatter in that case (the host shim checks)
+ * Scores are sum_j exp(double(sim_j) / double(t)) accumulated in rank order.
+ */
+int b200knn_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
+                 int64_t n_labels, int64_t label_offset, int C, double t,
+                 int64_t* pred, double* scores, int32_t* err_flag, void* stream);
+
+/* Device capability probe for the host shim: 1 if the current device is sm_100. */
+int b200knn_device_ok(void);
+
+/* How b200knn_topk decomposes a call (for the bench and the docs):
+ * out6 = {n_qtiles, splits, split_rows, n_items, grid, list_capacity}. HOST pointer. */
+int b200knn_plan_info(int mode, int64_t B, int64_t N, int dim, int k, int64_t* host_out6);
+
+/* TEST HOOK, not a product entry point: b200knn_topk for the tensor-core modes
+ * that also dumps the raw (B,N) fp32 similarity tiles it selected from, and a
+ * pipeline diagnostic word diag[4] written if a barrier wait times out. */
+int b200knn_debug_topk_dump(int mode, const void* q_hi, const void* q_lo,
+                            const void* bank_hi, const void* bank_lo, int64_t B,
+                            int64_t N, int dim, int k, uint64_t* out_keys,
+                            void* workspace, size_t workspace_bytes, float* dump,
+                            int32_t* diag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KNN_H_ */

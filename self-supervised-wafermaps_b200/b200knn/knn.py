@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference interface for the kNN hot path.
+
+``knn_predict`` keeps the exact signature, defaults, tensor layouts and return
+type of ``lightly.utils.benchmarking.knn_predict`` as the reference binds and
+calls it (``src/ssl_wafermap/models/knn.py:16`` import, ``:91-98`` and
+``:205-212`` calls): ``feature`` (B,D), ``feature_bank`` (D,N) — the
+``.t().contiguous()`` layout of ``knn.py:80`` — ``feature_labels`` (N,) int64,
+returning (B, num_classes) int64 class rankings whose column 0 the caller
+consumes (``knn.py:99``).  No normalisation happens inside (the caller does it,
+``knn.py:77`` / ``:90``).
+
+``knn_topk`` is the additive retrieval entry point (``torch.mm(...).topk(k)``
+with the canonical (sim desc, index asc) order) that generalises the
+notebooks' brute-force search
+(``notebooks/2.0-Figures-nearest-neighbors.ipynb:54``).
+
+Everything here is plumbing: argument checks that mirror torch's errors,
+operand-preparation caching, workspace allocation through the PyTorch caching
+allocator, and calls through the C ABI on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+_default_mode = os.environ.get("B200KNN_MODE", "exact")
+
+# Measurement hook (bench.py): when set to a list, every b200knn_topk C call is bracketed by
+# CUDA events recorded on the launching stream and the (start, end) pair is appended.
+profile_events = None
+
+
+def set_default_mode(mode: str) -> None:
+    """Select the similarity mode ``knn_predict``/``knn_topk`` use when none is passed.
+
+    ``"exact"``  fp32 CUDA-core contraction, sequential-fma similarities (bitwise reproducible);
+    ``"tf32x3"`` tcgen05 hi/lo-split TF32, fp32-class accuracy;
+    ``"bf16"``   tcgen05 BF16 operands / fp32 accumulate (fastest; recall@k reported by bench).
+    """
+    global _default_mode
+    if mode not in _lib.MODES:
+        raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(_lib.MODES)}")
+    _default_mode = mode
+
+
+def get_default_mode() -> str:
+    return _default_mode
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(name: str, t: torch.Tensor) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"b200knn: {name} is on {t.device}; this path runs on sm_100a CUDA tensors only "
+            "(no CPU fallback by design)"
+        )
+
+
+def padded_dim(dim: int) -> int:
+    return (dim + 63) // 64 * 64
+
+
+# ----------------------------------------------------------------------------
+# operand preparation (+ cache for the bank, which the reference rebuilds once
+# per validation epoch and then reuses for every validation step, knn.py:67-98)
+# ----------------------------------------------------------------------------
+class PreparedRows:
+    """K-major rows in the layout the tensor-core kernel streams with TMA."""
+
+    __slots__ = ("mode", "n", "dim", "hi", "lo")
+
+    def __init__(self, mode: str, n: int, dim: int, hi: torch.Tensor, lo: Optional[torch.Tensor]):
+        self.mode, self.n, self.dim, self.hi, self.lo = mode, n, dim, hi, lo
+
+
+def _layout_of(x: torch.Tensor, vectors_are_columns: bool) -> Tuple[torch.Tensor, int, int]:
+    """Return (tensor, layout, ld) describing n vectors of dimension dim without copying
+    when the strides allow it.  vectors_are_columns: x is (D, N) (bank); else (N, D)."""
+    if vectors_are_columns:
+        if x.stride(1) == 1 and x.stride(0) >= max(1, x.shape[1]):
+            return x, _lib.LAYOUT_DN, x.stride(0)
+        if x.stride(0) == 1 and x.stride(1) >= max(1, x.shape[0]):  # a .t() view of an (N, D) tensor
+            return x, _lib.LAYOUT_ND, x.stride(1)
+        x = x.contiguous()
+        return x, _lib.LAYOUT_DN, x.stride(0)
+    if x.stride(1) == 1 and x.stride(0) >= max(1, x.shape[1]):
+        return x, _lib.LAYOUT_ND, x.stride(0)
+    if x.stride(0) == 1 and x.stride(1) >= max(1, x.shape[0]):
+        return x, _lib.LAYOUT_DN, x.stride(1)
+    x = x.contiguous()
+    return x, _lib.LAYOUT_ND, x.stride(0)
+
+
+def prepare_rows(x: torch.Tensor, mode: str, vectors_are_columns: bool) -> PreparedRows:
+    lib = _lib.load()
+    if x.dtype not in _DTYPES:
+        x = x.float()
+    n, dim = (x.shape[1], x.shape[0]) if vectors_are_columns else (x.shape[0], x.shape[1])
+    x, layout, ld = _layout_of(x, vectors_are_columns)
+    dpad = padded_dim(dim)
+    if mode == "bf16":
+        hi = torch.empty((n, dpad), dtype=torch.bfloat16, device=x.device)
+        lo = None
+    elif mode == "tf32x3":
+        hi = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
+        lo = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
+    else:
+        raise ValueError(f"mode {mode!r} takes caller tensors directly")
+    if n > 0:
+        _lib.check(
+            lib.b200knn_prepare_rows(x.data_ptr(), _DTYPES[x.dtype], layout, n, dim, ld,
+                                     _lib.MODES[mode], hi.data_ptr(), _ptr(lo), _stream()),
+            "prepare_rows",
+        )
+    return PreparedRows(mode, n, dim, hi, lo)
+
+
+class _BankCache:
+    """Prepared banks keyed on the identity *and version* of the caller's tensor, so an
+    in-place update or a rebuilt bank (new validation epoch) is re-prepared."""
+
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self._entries = {}
+
+    def get(self, bank: torch.Tensor, mode: str) -> PreparedRows:
+        key = (bank.data_ptr(), bank._version, tuple(bank.shape), tuple(bank.stride()), bank.dtype,
+               bank.device.index, mode)
+        hit = self._entries.get(key)
+        if hit is not None and hit[0]() is not None:
+            return hit[1]
+        prep = prepare_rows(bank, mode, vectors_are_columns=True)
+        if len(self._entries) >= self.capacity:
+            self._entries.pop(next(iter(self._entries)))
+        try:
+            ref = weakref.ref(bank)
+        except TypeError:  # pragma: no cover
+            ref = lambda: bank  # noqa: E731
+        self._entries[key] = (ref, prep)
+        return prep
+
+    def clear(self) -> None:
+        self._entries.clear()
+
+
+bank_cache = _BankCache()
+
+
+# ----------------------------------------------------------------------------
+# selection keys
+# ----------------------------------------------------------------------------
+def _check_feature_bank(feature: torch.Tensor, feature_bank: torch.Tensor) -> None:
+    _require_cuda("feature", feature)
+    _require_cuda("feature_bank", feature_bank)
+    if feature.device != feature_bank.device:
+        raise RuntimeError("Expected all tensors to be on the same device, but found "
+                           f"{feature.device} and {feature_bank.device}")
+    if feature.dim() != 2:
+        raise RuntimeError("self must be a matrix")  # torch.mm's message (knn.py:89 .squeeze() hazard)
+    if feature_bank.dim() != 2:
+        raise RuntimeError("mat2 must be a matrix")
+    if feature.shape[1] != feature_bank.shape[0]:
+        raise RuntimeError(
+            f"mat1 and mat2 shapes cannot be multiplied ({feature.shape[0]}x{feature.shape[1]} and "
+            f"{feature_bank.shape[0]}x{feature_bank.shape[1]})"
+        )
+
+
+def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: Optional[str] = None,
+              idx_offset: int = 0) -> torch.Tensor:
+    """(B,k) selection keys (uint64 bit patterns in an int64 tensor), sorted descending under
+    the canonical (sim desc, bank index asc) order; bank indices are offset by idx_offset."""
+    lib = _lib.load()
+    mode = mode or _default_mode
+    if mode not in _lib.MODES:
+        raise ValueError(f"unknown mode {mode!r}")
+    _check_feature_bank(feature, feature_bank)
+    B, D = feature.shape
+    N = feature_bank.shape[1]
+    k = int(k)
+    if k <= 0 or k > N:
+        raise RuntimeError("selected index k out of range")  # Tensor.topk's message
+    dev = feature.device
+    with torch.cuda.device(dev):
+        keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+        if B == 0:
+            return keys
+        ws_bytes = lib.b200knn_topk_workspace_bytes(B, N, D, k, _lib.MODES[mode])
+        if ws_bytes == 0:
+            raise RuntimeError(f"b200knn: unsupported problem (B={B}, N={N}, D={D}, k={k})")
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        ev = None
+        if mode != "exact":
+            pb = bank_cache.get(feature_bank, mode)
+            pq = prepare_rows(feature, mode, vectors_are_columns=False)
+        if profile_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        if mode == "exact":
+            q = feature if feature.dtype in _DTYPES else feature.float()
+            if q.stride(1) != 1:
+                q = q.contiguous()
+            bank = feature_bank if feature_bank.dtype in _DTYPES else feature_bank.float()
+            bank, layout, ld = _layout_of(bank, vectors_are_columns=True)
+            rc = lib.b200knn_topk(_lib.MODE_EXACT, q.data_ptr(), None, _DTYPES[q.dtype], q.stride(0),
+                                  bank.data_ptr(), None, _DTYPES[bank.dtype], layout, ld,
+                                  B, N, D, k, idx_offset, keys.data_ptr(), ws.data_ptr(), ws_bytes,
+                                  _stream())
+        else:
+            rc = lib.b200knn_topk(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), 0, 0,
+                                  pb.hi.data_ptr(), _ptr(pb.lo), 0, 0, 0,
+                                  B, N, D, k, idx_offset, keys.data_ptr(), ws.data_ptr(), ws_bytes,
+                                  _stream())
+        if ev is not None:
+            ev[1].record()
+            profile_events.append(ev)
+        _lib.check(rc, "topk")
+    return keys
+
+
+def decode_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    sims = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+    idx = torch.empty(keys.shape, dtype=torch.int64, device=keys.device)
+    if keys.numel():
+        with torch.cuda.device(keys.device):
+            _lib.check(lib.b200knn_decode_keys(keys.data_ptr(), keys.numel(), sims.data_ptr(),
+                                               idx.data_ptr(), _stream()), "decode_keys")
+    return sims, idx
+
+
+def merge_keys(keys_in: torch.Tensor, k_out: int) -> torch.Tensor:
+    """(G,B,k_in) sorted candidate lists -> (B,k_out): the shard-merge step."""
+    lib = _lib.load()
+    _require_cuda("keys_in", keys_in)
+    G, B, k_in = keys_in.shape
+    keys_in = keys_in.contiguous()
+    out = torch.empty((B, k_out), dtype=torch.int64, device=keys_in.device)
+    if B:
+        with torch.cuda.device(keys_in.device):
+            _lib.check(lib.b200knn_merge(keys_in.data_ptr(), G, B, k_in, k_out, out.data_ptr(),
+                                         _stream()), "merge")
+    return out
+
+
+def vote(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn_t: float,
+         label_offset: int = 0, return_scores: bool = False, check_labels: bool = True):
+    """keys (B,k) + labels (N,) -> (B,C) int64 class ranking (score desc, class asc)."""
+    lib = _lib.load()
+    _require_cuda("feature_labels", feature_labels)
+    B, k = keys.shape
+    labels = feature_labels
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    labels = labels.contiguous().view(-1)
+    C = int(num_classes)
+    dev = keys.device
+    pred = torch.empty((B, C), dtype=torch.int64, device=dev)
+    scores = torch.empty((B, C), dtype=torch.float64, device=dev) if return_scores else None
+    if B:
+        with torch.cuda.device(dev):
+            flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+            _lib.check(lib.b200knn_vote(keys.data_ptr(), labels.data_ptr(), B, k, labels.numel(),
+                                        label_offset, C, float(knn_t), pred.data_ptr(), _ptr(scores),
+                                        flag.data_ptr(), _stream()), "vote")
+            if check_labels:
+                f = int(flag.item())
+                if f == 1:
+                    # the reference raises here from zeros(...).scatter(...) (lightly knn_predict)
+                    raise RuntimeError("index out of bounds: a feature_labels entry is outside "
+                                       f"[0, num_classes={C})")
+                if f == 2:
+                    raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
+    return (pred, scores) if return_scores else pred
+
+
+# ----------------------------------------------------------------------------
+# the reference's public symbols for this path
+# ----------------------------------------------------------------------------
+def knn_predict(feature: torch.Tensor, feature_bank: torch.Tensor, feature_labels: torch.Tensor,
+                num_classes: int, knn_k: int = 200, knn_t: float = 0.1) -> torch.Tensor:
+    """Drop-in for ``lightly.utils.benchmarking.knn_predict`` (reference call sites
+    ``src/ssl_wafermap/models/knn.py:91-98``, ``:205-212``).
+
+    Args and return value are the reference's: feature (B,D), feature_bank (D,N),
+    feature_labels (N,), returns (B, num_classes) int64 with the predicted class in
+    column 0.  Neighbour order is (similarity desc, bank index asc); class order is
+    (score desc, class id asc).
+    """
+    _require_cuda("feature_labels", feature_labels)
+    keys = topk_keys(feature, feature_bank, knn_k)
+    if feature_labels.numel() != feature_bank.shape[1]:
+        raise RuntimeError(
+            f"feature_labels has {feature_labels.numel()} entries for a bank of {feature_bank.shape[1]}")
+    return vote(keys, feature_labels, num_classes, knn_t)
+
+
+def knn_topk(feature: torch.Tensor, feature_bank: torch.Tensor, k: int,
+             mode: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``torch.mm(feature, feature_bank).topk(k, dim=-1)`` without materialising the
+    similarity matrix: (sims fp32 (B,k) sorted desc, idx int64 (B,k)), ties by lowest index."""
+    return decode_keys(topk_keys(feature, feature_bank, k, mode))
+
+
+def plan_info(B: int, N: int, D: int, k: int, mode: Optional[str] = None) -> dict:
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 6)()
+    _lib.check(lib.b200knn_plan_info(_lib.MODES[mode or _default_mode], B, N, D, k, out), "plan_info")
+    names = ("n_qtiles", "splits", "split_rows", "n_items", "grid", "list_capacity")
+    return dict(zip(names, [int(v) for v in out]))

@@ -1,0 +1,229 @@
+// api.cu — the extern "C" boundary declared in include/b200knn.h.
+// Argument validation, work planning, workspace carving, kernel dispatch.
+// No device allocation, no implicit synchronisation, no exceptions.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/b200knn.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "plan.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  std::snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+int fail_cuda(const char* where, cudaError_t e) {
+  std::snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return B200KNN_E_CUDA;
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan* plan) {
+  const int cap = b200knn::list_capacity(k);
+  if (cap == 0) return false;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  if (mode == B200KNN_MODE_EXACT) {
+    *plan = b200knn::make_plan(B, N, k, cap, 128, 128, sms * 2);
+  } else {
+    *plan = b200knn::make_plan(B, N, k, cap, 128, b200knn::tc_tile_n(mode, dim), sms);
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200knn_version(void) { return B200KNN_VERSION; }
+const char* b200knn_last_error(void) { return g_err; }
+
+int b200knn_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout, int64_t n_vec, int dim,
+                         int64_t ld, int mode, void* dst_hi, void* dst_lo, void* stream) {
+  if (!src || !dst_hi || n_vec < 0 || dim <= 0) return fail(B200KNN_E_ARG, "prepare_rows: bad argument");
+  if (src_dtype < B200KNN_F32 || src_dtype > B200KNN_BF16)
+    return fail(B200KNN_E_ARG, "prepare_rows: unknown dtype");
+  if (src_layout != B200KNN_LAYOUT_DN && src_layout != B200KNN_LAYOUT_ND)
+    return fail(B200KNN_E_ARG, "prepare_rows: unknown layout");
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3)
+    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16 or TF32X3");
+  if (mode == B200KNN_MODE_TF32X3 && !dst_lo)
+    return fail(B200KNN_E_ARG, "prepare_rows: TF32X3 needs dst_lo");
+  cudaError_t e = b200knn::launch_prepare(src, src_dtype, src_layout, n_vec, dim, ld, mode, dst_hi,
+                                          dst_lo, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("prepare_rows", e);
+}
+
+size_t b200knn_topk_workspace_bytes(int64_t B, int64_t N, int dim, int k, int mode) {
+  b200knn::TopkPlan plan;
+  if (B <= 0 || N <= 0 || k <= 0 || !plan_for(mode, B, N, dim, k, &plan)) return 0;
+  return plan.total_bytes + 256;
+}
+
+static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, int64_t q_ld,
+                     const void* bank_hi, const void* bank_lo, int bank_dtype, int bank_layout,
+                     int64_t bank_ld, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
+                     uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream,
+                     float* dump, int32_t* diag) {
+  if (B < 0 || N <= 0 || dim <= 0) return fail(B200KNN_E_ARG, "topk: bad shape");
+  if (k <= 0 || k > N) return fail(B200KNN_E_ARG, "topk: selected index k out of range");
+  if (N + idx_offset >= 0xFFFFFFFFll || idx_offset < 0)
+    return fail(B200KNN_E_ARG, "topk: bank index does not fit 32 bits");
+  if (B == 0) return B200KNN_OK;
+  if (!q_hi || !bank_hi || !out_keys || !workspace) return fail(B200KNN_E_ARG, "topk: null pointer");
+  b200knn::TopkPlan plan;
+  if (!plan_for(mode, B, N, dim, k, &plan)) return fail(B200KNN_E_UNSUPPORTED, "topk: k too large (max 992)");
+  uintptr_t ws = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  const size_t slack = ws - reinterpret_cast<uintptr_t>(workspace);
+  if (workspace_bytes < plan.total_bytes + slack) return fail(B200KNN_E_WORKSPACE, "topk: workspace too small");
+  uint64_t* lists = reinterpret_cast<uint64_t*>(ws);
+  uint64_t* partial = plan.splits > 1 ? reinterpret_cast<uint64_t*>(ws + plan.lists_bytes) : out_keys;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (mode == B200KNN_MODE_EXACT) {
+    if (q_dtype < 0 || q_dtype > 2 || bank_dtype < 0 || bank_dtype > 2)
+      return fail(B200KNN_E_ARG, "topk: unknown dtype");
+    b200knn::ExactParams p;
+    p.q = q_hi;
+    p.q_dtype = q_dtype;
+    p.q_ld = q_ld;
+    p.bank = bank_hi;
+    p.bank_dtype = bank_dtype;
+    if (bank_layout == B200KNN_LAYOUT_DN) {
+      p.bank_sd = bank_ld;
+      p.bank_sn = 1;
+    } else if (bank_layout == B200KNN_LAYOUT_ND) {
+      p.bank_sd = 1;
+      p.bank_sn = bank_ld;
+    } else {
+      return fail(B200KNN_E_ARG, "topk: unknown bank layout");
+    }
+    p.B = B;
+    p.N = N;
+    p.D = dim;
+    p.k = k;
+    p.idx_offset = idx_offset;
+    p.n_qtiles = plan.n_qtiles;
+    p.n_items = plan.n_items;
+    p.split_rows = plan.split_rows;
+    p.lists = lists;
+    p.out = partial;
+    e = b200knn::launch_exact(p, plan.grid, plan.cap, st);
+    if (e != cudaSuccess) return fail_cuda("topk(exact)", e);
+  } else if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_TF32X3) {
+    if (mode == B200KNN_MODE_TF32X3 && (!q_lo || !bank_lo))
+      return fail(B200KNN_E_ARG, "topk: TF32X3 needs the lo operands");
+    b200knn::TcParams p;
+    p.mode = mode;
+    p.q_hi = q_hi;
+    p.q_lo = q_lo;
+    p.bank_hi = bank_hi;
+    p.bank_lo = bank_lo;
+    p.B = B;
+    p.N = N;
+    p.D = dim;
+    p.k = k;
+    p.idx_offset = idx_offset;
+    p.n_qtiles = plan.n_qtiles;
+    p.n_items = plan.n_items;
+    p.split_rows = plan.split_rows;
+    p.lists = lists;
+    p.out = partial;
+    const char* why = "";
+    e = b200knn::launch_tc(p, plan.grid, plan.cap, st, dump, diag, &why);
+    if (e == cudaErrorNotSupported) return fail(B200KNN_E_UNSUPPORTED, "topk(tc): %s", why);
+    if (e != cudaSuccess) {
+      std::snprintf(g_err, sizeof(g_err), "topk(tc): %s %s", cudaGetErrorString(e), why);
+      return B200KNN_E_CUDA;
+    }
+  } else {
+    return fail(B200KNN_E_ARG, "topk: unknown mode");
+  }
+  if (plan.splits > 1) {
+    e = b200knn::launch_merge(partial, plan.splits, B, k, k, out_keys, st);
+    if (e != cudaSuccess) return fail_cuda("topk(merge)", e);
+  }
+  return B200KNN_OK;
+}
+
+int b200knn_topk(int mode, const void* q_hi, const void* q_lo, int q_dtype, int64_t q_ld,
+                 const void* bank_hi, const void* bank_lo, int bank_dtype, int bank_layout,
+                 int64_t bank_ld, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
+                 uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream) {
+  return topk_impl(mode, q_hi, q_lo, q_dtype, q_ld, bank_hi, bank_lo, bank_dtype, bank_layout,
+                   bank_ld, B, N, dim, k, idx_offset, out_keys, workspace, workspace_bytes, stream,
+                   nullptr, nullptr);
+}
+
+// Test hook (not part of the product path): same as b200knn_topk for the tensor-core
+// modes, additionally dumping the raw (B,N) fp32 similarity tiles and the pipeline
+// diagnostic word.  Used by tests/ to validate the MMA path against a plain GEMM.
+int b200knn_debug_topk_dump(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
+                            const void* bank_lo, int64_t B, int64_t N, int dim, int k,
+                            uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                            float* dump, int32_t* diag, void* stream) {
+  return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, N, dim, k, 0, out_keys,
+                   workspace, workspace_bytes, stream, dump, diag);
+}
+
+// Plan introspection for the host shim / bench (how the work was split).
+int b200knn_plan_info(int mode, int64_t B, int64_t N, int dim, int k, int64_t* out6) {
+  b200knn::TopkPlan plan;
+  if (!out6 || !plan_for(mode, B, N, dim, k, &plan)) return fail(B200KNN_E_ARG, "plan_info: bad argument");
+  out6[0] = plan.n_qtiles;
+  out6[1] = plan.splits;
+  out6[2] = plan.split_rows;
+  out6[3] = plan.n_items;
+  out6[4] = plan.grid;
+  out6[5] = plan.cap;
+  return B200KNN_OK;
+}
+
+int b200knn_merge(const uint64_t* keys_in, int G, int64_t B, int k_in, int k_out, uint64_t* keys_out,
+                  void* stream) {
+  if (!keys_in || !keys_out || G <= 0 || B < 0 || k_in <= 0 || k_out <= 0)
+    return fail(B200KNN_E_ARG, "merge: bad argument");
+  if (int64_t(k_out) > int64_t(G) * k_in) return fail(B200KNN_E_ARG, "merge: k_out > G*k_in");
+  if (b200knn::list_capacity(k_out) == 0) return fail(B200KNN_E_UNSUPPORTED, "merge: k too large (max 992)");
+  cudaError_t e = b200knn::launch_merge(keys_in, G, B, k_in, k_out, keys_out,
+                                        static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("merge", e);
+}
+
+int b200knn_decode_keys(const uint64_t* keys, int64_t n_keys, float* sims, int64_t* idx, void* stream) {
+  if (!keys || n_keys < 0) return fail(B200KNN_E_ARG, "decode_keys: bad argument");
+  cudaError_t e = b200knn::launch_decode(keys, n_keys, sims, idx, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("decode_keys", e);
+}
+
+int b200knn_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k, int64_t n_labels,
+                 int64_t label_offset, int C, double t, int64_t* pred, double* scores,
+                 int32_t* err_flag, void* stream) {
+  if (!keys || !labels || !pred || !err_flag || B < 0 || k <= 0 || C <= 0 || n_labels <= 0)
+    return fail(B200KNN_E_ARG, "vote: bad argument");
+  if (!(t > 0.0) && !(t < 0.0)) return fail(B200KNN_E_ARG, "vote: temperature must be non-zero");
+  cudaError_t e = b200knn::launch_vote(keys, labels, B, k, n_labels, label_offset, C, t, pred, scores,
+                                       err_flag, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidValue) return fail(B200KNN_E_UNSUPPORTED, "vote: k/num_classes too large for shared memory");
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("vote", e);
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// common.cuh — selection keys, warp bitonic sort and the streaming per-row top-k
+// state shared by every similarity kernel (exact fp32 and tcgen05 paths).
+//
+// Canonical total order: neighbours are ranked by
+// (sim desc, bank index asc).  A 64-bit key makes that one integer compare:
+//     key = orderable_u32(sim) << 32 | (0xFFFFFFFF - idx)      larger = better
+// This replaces the unspecified tie order of Tensor.topk in lightly's
+// knn_predict (call site: src/ssl_wafermap/models/knn.py:91-98).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200knn {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t f32_to_orderable(float s) {
+  s = s + 0.0f;  // -0.0 -> +0.0 so that equal values compare equal
+  uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float orderable_to_f32(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t make_key(float s, uint32_t idx) {
+  return (uint64_t(f32_to_orderable(s)) << 32) | uint64_t(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_sim(uint64_t key) {
+  return key == 0 ? __int_as_float(0xff800000)  // empty slot -> -inf
+                  : orderable_to_f32(uint32_t(key >> 32));
+}
+__device__ __forceinline__ int64_t key_idx(uint64_t key) {
+  return key == 0 ? int64_t(-1) : int64_t(0xFFFFFFFFu - uint32_t(key & 0xFFFFFFFFu));
+}
+
+// Bitonic sort, descending, of ITEMS*32 keys held as v[r] on lane l <-> element
+// index r*32 + l.  Strides >= 32 are register-to-register, < 32 are shuffles.
+template <int ITEMS>
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[ITEMS], int lane) {
+  constexpr int N = ITEMS * 32;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int pr = r ^ (stride >> 5);
+          if (pr > r) {
+            const bool desc = (((r * 32) & size) == 0);
+            const uint64_t a = v[r], b = v[pr];
+            const bool sw = desc ? (a < b) : (a > b);
+            v[r] = sw ? b : a;
+            v[pr] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int i = r * 32 + lane;
+          const uint64_t other = __shfl_xor_sync(kFull, v[r], stride);
+          const bool desc = ((i & size) == 0);
+          const bool lower = ((lane & stride) == 0);
+          const bool keep_max = (desc == lower);
+          const uint64_t mx = v[r] > other ? v[r] : other;
+          const uint64_t mn = v[r] > other ? other : v[r];
+          v[r] = keep_max ? mx : mn;
+        }
+      }
+    }
+  }
+}
+
+// Smallest supported list capacity (power of two, multiple of 32) for a given k.
+// The capacity leaves slack above k so that a prune (sort + cut to k) happens
+// once per (cap - k - 32) insertions rather than per insertion.
+__host__ __device__ inline int list_capacity(int k) {
+  int cap = 64;
+  while (cap < 2 * k + 32 && cap < 1024) cap <<= 1;
+  if (cap < k + 32) cap = 0;  // k too large for the in-register sort (k <= 992)
+  return cap;
+}
+
+// Warp-cooperative prune of one row's candidate list (global scratch, `cap`
+// = ITEMS*32 slots, `n_valid` filled): sort descending, keep the best k in
+// place (sorted).  Returns the new admission threshold: the sim of the k-th
+// best, or -inf while fewer than k candidates exist.
+template <int ITEMS>
+__device__ __forceinline__ float warp_prune(uint64_t* list, int n_valid, int k, int lane) {
+  uint64_t v[ITEMS];
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int i = r * 32 + lane;
+    v[r] = (i < n_valid) ? list[i] : 0ull;
+  }
+  warp_sort_desc<ITEMS>(v, lane);
+  uint64_t kth = 0;
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int i = r * 32 + lane;
+    if (i < k) list[i] = v[r];
+    if (r == ((k - 1) >> 5)) kth = v[r];
+  }
+  kth = __shfl_sync(kFull, kth, (k - 1) & 31);
+  return (n_valid >= k && kth != 0) ? orderable_to_f32(uint32_t(kth >> 32))
+                                    : __int_as_float(0xff800000);
+}
+
+// Per-row streaming state owned by the row's scanning thread.
+struct RowState {
+  float tau;     // admit sims strictly greater than tau (ties lose: bank is scanned in ascending idx)
+  uint32_t cnt;  // filled slots of the row's list
+};
+
+// After a chunk of at most CHUNK appends per row: prune every row of the warp
+// whose list could overflow during the next chunk.  `lists` points at the
+// warp's first row; row r of the warp is lane r.
+template <int ITEMS, int CHUNK>
+__device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int k, int lane) {
+  constexpr int CAP = ITEMS * 32;
+  const bool need = (st.cnt + CHUNK > CAP);
+  unsigned m = __ballot_sync(kFull, need);
+  if (m == 0) return;
+  __syncwarp();  // owner's appends visible to the whole warp
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int n_valid = __shfl_sync(kFull, int(st.cnt), src);
+    const float t = warp_prune<ITEMS>(lists + size_t(src) * CAP, n_valid, k, lane);
+    if (lane == src) {
+      st.tau = t;
+      st.cnt = n_valid < k ? n_valid : k;
+    }
+  }
+  __syncwarp();
+}
+
+// End of a work item: every row of the warp is pruned one last time and its
+// best k keys (sorted descending, zero-padded) are written to `out` (row r of
+// the warp at out + r*out_stride) if row_valid.
+template <int ITEMS>
+__device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, int k, int lane,
+                                           uint64_t* out, size_t out_stride, unsigned valid_mask) {
+  constexpr int CAP = ITEMS * 32;
+  __syncwarp();
+  for (int src = 0; src < 32; ++src) {
+    if (!((valid_mask >> src) & 1u)) continue;
+    const int n_valid = __shfl_sync(kFull, int(st.cnt), src);
+    uint64_t* list = lists + size_t(src) * CAP;
+    uint64_t v[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = r * 32 + lane;
+      v[r] = (i < n_valid) ? list[i] : 0ull;
+    }
+    warp_sort_desc<ITEMS>(v, lane);
+    uint64_t* o = out + size_t(src) * out_stride;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = r * 32 + lane;
+      if (i < k) o[i] = v[r];
+    }
+  }
+  __syncwarp();
+}
+
+}  // namespace b200knn

@@ -1,0 +1,59 @@
+// kernels.h — internal launch interfaces between api.cu and the kernel files.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200knn {
+
+struct ExactParams {
+  const void* q;
+  int q_dtype;
+  int64_t q_ld;
+  const void* bank;
+  int bank_dtype;
+  int64_t bank_sd;  // element stride between consecutive d of one bank vector
+  int64_t bank_sn;  // element stride between consecutive bank vectors
+  int64_t B, N;
+  int D, k;
+  int64_t idx_offset;
+  int64_t n_qtiles, n_items, split_rows;
+  uint64_t* lists;
+  uint64_t* out;  // (splits, B, k)
+};
+
+cudaError_t launch_exact(const ExactParams& p, int grid, int cap, cudaStream_t stream);
+
+// merge G sorted lists per row: in (G,B,k_in) -> out (B,k_out)
+cudaError_t launch_merge(const uint64_t* in, int G, int64_t B, int k_in, int k_out, uint64_t* out,
+                         cudaStream_t stream);
+cudaError_t launch_decode(const uint64_t* keys, int64_t n, float* sims, int64_t* idx,
+                          cudaStream_t stream);
+cudaError_t launch_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
+                        int64_t n_labels, int64_t label_offset, int C, double t, int64_t* pred,
+                        double* scores, int32_t* err_flag, cudaStream_t stream);
+cudaError_t launch_prepare(const void* src, int src_dtype, int src_layout, int64_t n_vec, int dim,
+                           int64_t ld, int mode, void* dst_hi, void* dst_lo, cudaStream_t stream);
+
+// tensor-core path (tc_topk.cu)
+struct TcParams {
+  int mode;  // B200KNN_MODE_BF16 / TF32X3
+  const void* q_hi;
+  const void* q_lo;
+  const void* bank_hi;
+  const void* bank_lo;
+  int64_t B, N;
+  int D, k;
+  int64_t idx_offset;
+  int64_t n_qtiles, n_items, split_rows;
+  uint64_t* lists;
+  uint64_t* out;  // (splits, B, k)
+};
+// returns cudaErrorNotSupported if (D, k) is outside what the kernel handles
+// `dump` (optional, (B,N) fp32) receives the raw similarity tiles (unit tests only);
+// `diag` (optional, int32[4]) records which pipeline wait timed out before a trap.
+cudaError_t launch_tc(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
+                      int32_t* diag, const char** why);
+int tc_tile_n(int mode, int dim);
+
+}  // namespace b200knn

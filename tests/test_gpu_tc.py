@@ -1,0 +1,123 @@
+"""GPU: the tcgen05 tensor-core modes (bf16, tf32x3) through the C ABI.
+1. the raw similarity tiles (debug dump) against a plain fp32/fp64 GEMM of the SAME prepared
+   operands — validates TMA/UMMA descriptors and TMEM addressing;
+2. the fused selection against the canonical top-k of those dumped tiles — bit-exact;
+3. tf32x3 against the fp64 oracle under the §7.3 contract (1e-5 relative);
+4. bf16 recall@k against the fp64 oracle (stated, asserted >= 0.98 on these inputs)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import b200knn
+import datagen
+from b200knn import _lib
+from oracle import knn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def run_dump(q: np.ndarray, bank_dn: np.ndarray, k: int, mode: str):
+    lib = _lib.load()
+    tq, tb = _t(q), _t(bank_dn)
+    pq = b200knn.prepare_rows(tq, mode, vectors_are_columns=False)
+    pb = b200knn.prepare_rows(tb, mode, vectors_are_columns=True)
+    B, D = q.shape
+    N = bank_dn.shape[1]
+    keys = torch.zeros((B, k), dtype=torch.int64, device=DEV)
+    dump = torch.full((B, N), float("nan"), dtype=torch.float32, device=DEV)
+    diag = torch.zeros(4, dtype=torch.int32, device=DEV)
+    ws_bytes = lib.b200knn_topk_workspace_bytes(B, N, D, k, _lib.MODES[mode])
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    rc = lib.b200knn_debug_topk_dump(_lib.MODES[mode], pq.hi.data_ptr(), None if pq.lo is None else pq.lo.data_ptr(),
+                                     pb.hi.data_ptr(), None if pb.lo is None else pb.lo.data_ptr(),
+                                     B, N, D, k, keys.data_ptr(), ws.data_ptr(), ws_bytes, dump.data_ptr(),
+                                     diag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "debug_topk_dump")
+    torch.cuda.synchronize()
+    assert diag.cpu().tolist()[0] == 0, f"pipeline wait timed out: {diag.cpu().tolist()}"
+    return keys.cpu().numpy().view(np.uint64), dump.cpu().numpy(), pq, pb
+
+
+CASES = [
+    ("ragged", None),            # D=72 (padded to 128), N=1001, B=7: OOB rows/cols everywhere
+    ("k5", None),                # B=64, k=5
+    ("mixed38", None),           # k=20
+    ("clustered_d384", None),    # D=384, k=200
+    ("clustered_small", None),   # D=512, k=200, N=4096
+]
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("name,_", CASES)
+def test_tiles_and_selection(name, _, mode):
+    c = datagen.make_case(name)
+    q, bank, k = c["feature"], c["bank"], c["k"]
+    keys, dump, pq, pb = run_dump(q, bank, k, mode)
+    D = q.shape[1]
+    assert not np.isnan(dump).any(), "some similarity tile was never written"
+    if mode == "bf16":
+        qh = pq.hi.float().cpu().numpy()[:, :D].astype(np.float64)
+        bh = pb.hi.float().cpu().numpy()[:, :D].astype(np.float64)
+        ref = qh @ bh.T
+        tol = 2e-6  # fp32 accumulation of exact bf16 products
+    else:
+        qf = (pq.hi.double() + pq.lo.double()).cpu().numpy()[:, :D]
+        bf = (pb.hi.double() + pb.lo.double()).cpu().numpy()[:, :D]
+        assert np.array_equal(qf.astype(np.float32), q) and np.array_equal(bf.astype(np.float32), bank.T)
+        ref = qf @ bf.T
+        tol = 1e-5 * max(1.0, np.abs(ref).max())
+    err = np.abs(dump.astype(np.float64) - ref).max()
+    assert err <= tol, f"{mode} tile error {err}"
+    # selection is exact w.r.t. the tiles it saw
+    want_s, want_i = O.canonical_topk_c(dump, k)
+    assert np.array_equal(keys, O.make_keys(want_s, want_i))
+    # and the product entry point gives the same keys as the debug hook
+    again = b200knn.topk_keys(_t(q), _t(bank), k, mode=mode).cpu().numpy().view(np.uint64)
+    assert np.array_equal(again, keys)
+
+
+@pytest.mark.parametrize("name", ["clustered_small", "gauss_small", "mixed38"])
+def test_tf32x3_meets_fp32_contract(name):
+    c = datagen.make_case(name)
+    sims, idx = b200knn.knn_topk(_t(c["feature"]), _t(c["bank"]), c["k"], mode="tf32x3")
+    r = O.compare_topk(sims.cpu().numpy(), idx.cpu().numpy(), c["feature"], c["bank"], c["k"])
+    assert r["max_rel_err"] <= 1e-5
+    assert r["idx_mismatch_unambiguous"] == 0 and r["set_mismatch_rows_unambiguous"] == 0
+
+
+@pytest.mark.parametrize("name", ["clustered_small", "gauss_small"])
+def test_bf16_recall(name):
+    c = datagen.make_case(name)
+    sims, idx = b200knn.knn_topk(_t(c["feature"]), _t(c["bank"]), c["k"], mode="bf16")
+    r = O.compare_topk(sims.cpu().numpy(), idx.cpu().numpy(), c["feature"], c["bank"], c["k"])
+    print(f"bf16 recall@{c['k']} on {name}: {r['recall_at_k']:.4f}, max rel err {r['max_rel_err']:.2e}")
+    assert r["recall_at_k"] >= 0.98 and r["max_rel_err"] <= 2e-2
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+def test_large_bank_against_exact_mode(mode):
+    """Sizes the CPU oracle cannot cover: tensor-core modes against the on-device exact mode
+    (itself bit-checked against the oracle in test_gpu_exact.py) on a 811,457 x 512 bank."""
+    N, D, k, B = 811457, 512, 200, 256
+    g = torch.Generator(device=DEV).manual_seed(811)
+    bank = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device=DEV), dim=1).t().contiguous()
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device=DEV), dim=1)
+    es, ei = b200knn.knn_topk(q, bank, k, mode="exact")
+    ts, ti = b200knn.knn_topk(q, bank, k, mode=mode)
+    ei, ti = ei.cpu().numpy(), ti.cpu().numpy()
+    recall = np.mean([len(set(ei[b]) & set(ti[b])) / k for b in range(B)])
+    print(f"{mode} recall@{k} vs exact at N={N}: {recall:.5f}")
+    if mode == "tf32x3":
+        assert recall >= 0.9995 and float((es - ts).abs().max()) <= 1e-5
+        # batch invariance of the tensor-core path: same rows, smaller batch, identical keys
+        ts2, ti2 = b200knn.knn_topk(q[:64].contiguous(), bank, k, mode=mode)
+        assert torch.equal(ts2, ts[:64]) and np.array_equal(ti2.cpu().numpy(), ti[:64])
+    else:
+        assert recall >= 0.98

@@ -1,0 +1,97 @@
+"""CPU: host-side logic of the drop-in boundary — errors, install(), layout detection,
+shard bounds.  No compute calls (those are the -m gpu tests)."""
+import sys
+import types
+
+import pytest
+import torch
+
+import b200knn
+from b200knn import knn as K
+
+
+def test_signature_matches_reference_symbol():
+    import inspect
+
+    sig = inspect.signature(b200knn.knn_predict)
+    assert list(sig.parameters) == ["feature", "feature_bank", "feature_labels", "num_classes", "knn_k", "knn_t"]
+    assert sig.parameters["knn_k"].default == 200 and sig.parameters["knn_t"].default == 0.1
+
+
+def test_cpu_tensors_raise_no_fallback():
+    f, bank, lab = torch.randn(4, 8), torch.randn(8, 16), torch.zeros(16, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200knn.knn_predict(f, bank, lab, 3, 5, 0.1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200knn.knn_topk(f, bank, 5)
+
+
+def test_layout_detection():
+    bank = torch.randn(8, 16)  # (D,N) contiguous
+    t, layout, ld = K._layout_of(bank, True)
+    assert (layout, ld) == (K._lib.LAYOUT_DN, 16) and t.data_ptr() == bank.data_ptr()
+    nd = torch.randn(16, 8)
+    t, layout, ld = K._layout_of(nd.t(), True)  # a transposed view of an (N,D) matrix
+    assert (layout, ld) == (K._lib.LAYOUT_ND, 8) and t.data_ptr() == nd.data_ptr()
+    q = torch.randn(4, 8)
+    assert K._layout_of(q, False)[1:] == (K._lib.LAYOUT_ND, 8)
+    sl = torch.randn(8, 32)[:, ::2]  # non-unit stride -> copied
+    t, layout, ld = K._layout_of(sl, True)
+    assert t.is_contiguous() and (layout, ld) == (K._lib.LAYOUT_DN, 16)
+
+
+def test_modes():
+    assert b200knn.get_default_mode() in ("exact", "bf16", "tf32x3")
+    with pytest.raises(ValueError):
+        b200knn.set_default_mode("fp8")
+    old = b200knn.get_default_mode()
+    b200knn.set_default_mode("bf16")
+    assert b200knn.get_default_mode() == "bf16"
+    b200knn.set_default_mode(old)
+
+
+def test_install_rebinds_lightly_and_consumers():
+    """lightly is absent in this image: a stub package stands in for it, as the reference
+    imports it (src/ssl_wafermap/models/knn.py:16)."""
+    def orig(*a, **k):
+        return "lightly"
+
+    orig.__module__ = "lightly.utils.benchmarking"
+    pkgs = {}
+    for name in ("lightly", "lightly.utils", "lightly.utils.benchmarking"):
+        pkgs[name] = types.ModuleType(name)
+        pkgs[name].__path__ = []
+    pkgs["lightly.utils.benchmarking"].knn_predict = orig
+    consumer = types.ModuleType("ssl_wafermap.models.knn")
+    consumer.knn_predict = orig  # bound at import time by `from ... import knn_predict`
+    saved = {n: sys.modules.get(n) for n in list(pkgs) + ["ssl_wafermap.models.knn"]}
+    try:
+        sys.modules.update(pkgs)
+        sys.modules["ssl_wafermap.models.knn"] = consumer
+        done = b200knn.install()
+        assert done["lightly.utils.benchmarking"] and done["ssl_wafermap.models.knn"]
+        assert pkgs["lightly.utils.benchmarking"].knn_predict is b200knn.knn_predict
+        assert consumer.knn_predict is b200knn.knn_predict
+        b200knn.install()  # idempotent
+        b200knn.uninstall()
+        assert pkgs["lightly.utils.benchmarking"].knn_predict is orig and consumer.knn_predict is orig
+    finally:
+        b200knn.uninstall()
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+
+
+def test_shard_bounds_cover_and_are_disjoint():
+    for n in (0, 1, 7, 811457, 16777216):
+        for ws in (1, 2, 3, 4, 8):
+            spans = [b200knn.shard_bounds(n, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b and c <= d
+
+
+def test_padded_dim():
+    assert [K.padded_dim(d) for d in (1, 64, 72, 384, 512, 768)] == [64, 64, 128, 384, 512, 768]
