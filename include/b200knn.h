@@ -138,12 +138,14 @@ int b200knn_plan_info(int mode, int64_t B, int64_t N, int dim, int k, int64_t* h
 
 /* TEST HOOK, not a product entry point: b200knn_topk for the tensor-core modes
  * that also dumps the raw (B,N) fp32 similarity tiles it selected from, and a
- * pipeline diagnostic word diag[4] written if a barrier wait times out. */
+ * pipeline diagnostic word diag[4] written if a barrier wait times out.
+ * flags (experiments; results are then meaningless): 1 no selection, 2 no TMEM
+ * loads, 4 no MMA issue, 8 no bank TMA loads. */
 int b200knn_debug_topk_dump(int mode, const void* q_hi, const void* q_lo,
                             const void* bank_hi, const void* bank_lo, int64_t B,
                             int64_t N, int dim, int k, uint64_t* out_keys,
                             void* workspace, size_t workspace_bytes, float* dump,
-                            int32_t* diag, void* stream);
+                            int32_t* diag, int flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ SIGNATURES = {
     "b200knn_debug_topk_dump": (
         c_int,
         [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
-         c_void_p, c_size_t, c_void_p, c_void_p, c_void_p],
+         c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p],
     ),
 }
 

@@ -82,7 +82,7 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
                      const void* bank_hi, const void* bank_lo, int bank_dtype, int bank_layout,
                      int64_t bank_ld, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
                      uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream,
-                     float* dump, int32_t* diag) {
+                     float* dump, int32_t* diag, int flags) {
   if (B < 0 || N <= 0 || dim <= 0) return fail(B200KNN_E_ARG, "topk: bad shape");
   if (k <= 0 || k > N) return fail(B200KNN_E_ARG, "topk: selected index k out of range");
   if (N + idx_offset >= 0xFFFFFFFFll || idx_offset < 0)
@@ -148,7 +148,7 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.lists = lists;
     p.out = partial;
     const char* why = "";
-    e = b200knn::launch_tc(p, plan.grid, plan.cap, st, dump, diag, &why);
+    e = b200knn::launch_tc(p, plan.grid, plan.cap, st, dump, diag, flags, &why);
     if (e == cudaErrorNotSupported) return fail(B200KNN_E_UNSUPPORTED, "topk(tc): %s", why);
     if (e != cudaSuccess) {
       std::snprintf(g_err, sizeof(g_err), "topk(tc): %s %s", cudaGetErrorString(e), why);
@@ -170,7 +170,7 @@ int b200knn_topk(int mode, const void* q_hi, const void* q_lo, int q_dtype, int6
                  uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream) {
   return topk_impl(mode, q_hi, q_lo, q_dtype, q_ld, bank_hi, bank_lo, bank_dtype, bank_layout,
                    bank_ld, B, N, dim, k, idx_offset, out_keys, workspace, workspace_bytes, stream,
-                   nullptr, nullptr);
+                   nullptr, nullptr, 0);
 }
 
 // Test hook (not part of the product path): same as b200knn_topk for the tensor-core
@@ -179,9 +179,9 @@ int b200knn_topk(int mode, const void* q_hi, const void* q_lo, int q_dtype, int6
 int b200knn_debug_topk_dump(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
                             const void* bank_lo, int64_t B, int64_t N, int dim, int k,
                             uint64_t* out_keys, void* workspace, size_t workspace_bytes,
-                            float* dump, int32_t* diag, void* stream) {
+                            float* dump, int32_t* diag, int flags, void* stream) {
   return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, N, dim, k, 0, out_keys,
-                   workspace, workspace_bytes, stream, dump, diag);
+                   workspace, workspace_bytes, stream, dump, diag, flags);
 }
 
 // Plan introspection for the host shim / bench (how the work was split).

@@ -36,36 +36,51 @@ __device__ __forceinline__ int64_t key_idx(uint64_t key) {
 
 // Bitonic sort, descending, of ITEMS*32 keys held as v[r] on lane l <-> element
 // index r*32 + l.  Strides >= 32 are register-to-register, < 32 are shuffles.
+// The (size, stride) loops are deliberately NOT unrolled: a fully unrolled
+// 512-key network is ~120 KB of SASS that is executed once per prune and
+// thrashes the instruction cache (measured: stall_no_instruction was the top
+// stall reason of the fused kernel); rolled, the body is a few hundred
+// instructions that stay resident.
+template <int ITEMS, int D>
+__device__ __forceinline__ void sort_stage_inreg(uint64_t (&v)[ITEMS], int size) {
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int pr = r ^ D;
+    if (pr > r && pr < ITEMS) {
+      const bool desc = (((r * 32) & size) == 0);
+      const uint64_t a = v[r], b = v[pr];
+      const bool sw = desc ? (a < b) : (a > b);
+      v[r] = sw ? b : a;
+      v[pr] = sw ? a : b;
+    }
+  }
+}
+
 template <int ITEMS>
 __device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[ITEMS], int lane) {
   constexpr int N = ITEMS * 32;
-#pragma unroll
+#pragma unroll 1
   for (int size = 2; size <= N; size <<= 1) {
-#pragma unroll
+#pragma unroll 1
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       if (stride >= 32) {
-#pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
-          const int pr = r ^ (stride >> 5);
-          if (pr > r) {
-            const bool desc = (((r * 32) & size) == 0);
-            const uint64_t a = v[r], b = v[pr];
-            const bool sw = desc ? (a < b) : (a > b);
-            v[r] = sw ? b : a;
-            v[pr] = sw ? a : b;
-          }
+        switch (stride >> 5) {
+          case 1: sort_stage_inreg<ITEMS, 1>(v, size); break;
+          case 2: sort_stage_inreg<ITEMS, 2>(v, size); break;
+          case 4: sort_stage_inreg<ITEMS, 4>(v, size); break;
+          case 8: sort_stage_inreg<ITEMS, 8>(v, size); break;
+          default: sort_stage_inreg<ITEMS, 16>(v, size); break;
         }
       } else {
+        const bool lower = ((lane & stride) == 0);
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
           const int i = r * 32 + lane;
           const uint64_t other = __shfl_xor_sync(kFull, v[r], stride);
           const bool desc = ((i & size) == 0);
-          const bool lower = ((lane & stride) == 0);
           const bool keep_max = (desc == lower);
-          const uint64_t mx = v[r] > other ? v[r] : other;
-          const uint64_t mn = v[r] > other ? other : v[r];
-          v[r] = keep_max ? mx : mn;
+          const bool gt = v[r] > other;
+          v[r] = (gt == keep_max) ? v[r] : other;
         }
       }
     }
@@ -100,7 +115,7 @@ __device__ __forceinline__ float warp_prune(uint64_t* list, int n_valid, int k, 
   for (int r = 0; r < ITEMS; ++r) {
     const int i = r * 32 + lane;
     if (i < k) list[i] = v[r];
-    if (r == ((k - 1) >> 5)) kth = v[r];
+    kth = (i == k - 1) ? v[r] : kth;  // lane-dependent select: stays in registers
   }
   kth = __shfl_sync(kFull, kth, (k - 1) & 31);
   return (n_valid >= k && kth != 0) ? orderable_to_f32(uint32_t(kth >> 32))

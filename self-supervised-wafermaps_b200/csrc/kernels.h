@@ -53,7 +53,7 @@ struct TcParams {
 // `dump` (optional, (B,N) fp32) receives the raw similarity tiles (unit tests only);
 // `diag` (optional, int32[4]) records which pipeline wait timed out before a trap.
 cudaError_t launch_tc(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
-                      int32_t* diag, const char** why);
+                      int32_t* diag, int flags, const char** why);
 int tc_tile_n(int mode, int dim);
 
 }  // namespace b200knn

@@ -7,11 +7,18 @@
 // time, double buffered, drained by the epilogue warps straight into the
 // per-row candidate lists of common.cuh.
 //
-// CTA = 6 warps, one CTA per SM, persistent over work items
+// CTA = 10 warps, one CTA per SM, persistent over work items
 // (query tile of 128 rows) x (bank split):
 //   warp 0  : TMA producer  (one elected lane)   global -> smem, SWIZZLE_128B
 //   warp 1  : tcgen05.mma issuer (one lane); owns the TMEM allocation
-//   warp 2-5: epilogue; warp w drains TMEM lanes 32*(w%4)..+31 = query rows
+//   warp 2-9: epilogue; warp w may only touch TMEM lanes 32*(w%4)..+31, so two
+//             warps share each lane quarter and each owns 16 of its 32 query
+//             rows (two warps per scheduler hide each other's latencies; the
+//             selection code is latency-bound, measured CPI 8 with one warp).
+// Candidate extraction is warp-cooperative: a row whose 32-column chunk holds a
+// similarity above its threshold is staged through 128 B of shared memory so
+// that lane j tests column j (one ballot, coalesced appends), instead of one
+// thread walking its 32 registers through 32 divergent branches.
 // Pipelines (mbarrier): smem stage full/empty (TMA <-> MMA), TMEM accumulator
 // full/empty (MMA <-> epilogue), query tile full/empty (BF16 mode keeps the
 // 128 x D query tile resident in smem for the whole work item).
@@ -30,16 +37,25 @@
 #include "ptx.cuh"
 
 namespace b200knn {
+
+int tc_tile_n(int mode, int dim) {
+  if (mode == B200KNN_MODE_BF16) return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
+  return 128;
+}
+
 namespace {
 
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kRowBytes = 128;                   // one swizzle row = one k-block of a vector
 constexpr int kABlockBytes = kTileM * kRowBytes;  // 16 KB: 128 query rows x one k-block
-constexpr int kThreads = 192;
+constexpr int kEpiPerQuarter = 2;  // epilogue warps per TMEM lane quarter
+constexpr int kEpiWarps = 4 * kEpiPerQuarter;
+constexpr int kRowsPerWarp = 32 / kEpiPerQuarter;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemLimit = 232448;  // 227 KB
 
-struct alignas(8) Barriers {
+struct alignas(16) Barriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
@@ -48,6 +64,7 @@ struct alignas(8) Barriers {
   uint64_t q_empty;
   uint32_t tmem_base;
   uint32_t pad;
+  alignas(16) float stage[kEpiWarps][32];  // per epilogue warp: one row's 32-column chunk, lane j <-> column j
 };
 
 struct TcKernelArgs {
@@ -61,9 +78,11 @@ struct TcKernelArgs {
   uint64_t* out;
   float* dump;  // optional (B, N) fp32 similarity dump for unit tests (nullptr in production)
   int32_t* diag;
+  int flags;    // experiment switches of the debug entry point (0 in production):
+                // 1 no selection, 2 no TMEM loads, 4 no MMA issue, 8 no bank TMA loads
 };
 
-template <int MODE, int BLOCK_N, int ITEMS>
+template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG>
 __global__ void __launch_bounds__(kThreads, 1)
     tc_topk_kernel(const __grid_constant__ CUtensorMap map_q_hi,
                    const __grid_constant__ CUtensorMap map_q_lo,
@@ -102,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[b]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[b]), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[b]), kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::mbar_init(ptx::smem_u32(&bars->q_full), 1);
     ptx::mbar_init(ptx::smem_u32(&bars->q_empty), 1);
@@ -140,10 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, a.diag, 2);
             const uint32_t full = ptx::smem_u32(&bars->full[stage]);
             uint8_t* st = stage_smem + size_t(stage) * kStageBytes;
-            ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
-            if (kBf16) {
+            if (DEBUG && (a.flags & 8)) {
+              ptx::mbar_arrive(full);
+            } else if (kBf16) {
+              ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
               ptx::tma_load_2d(ptx::smem_u32(st), &map_b_hi, kb * kElemsPerRow, int(n0), full);
             } else {
+              ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
               ptx::tma_load_2d(ptx::smem_u32(st), &map_q_hi, kb * kElemsPerRow, m0, full);
               ptx::tma_load_2d(ptx::smem_u32(st + kABlockBytes), &map_q_lo, kb * kElemsPerRow, m0,
                                full);
@@ -183,7 +205,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase, a.diag, 5);
             ptx::tc_fence_after();
             const uint32_t st = ptx::smem_u32(stage_smem + size_t(stage) * kStageBytes);
-            if (kBf16) {
+            if (DEBUG && (a.flags & 4)) {
+            } else if (kBf16) {
               const uint32_t qa = ptx::smem_u32(q_smem + kb * kABlockBytes);
 #pragma unroll
               for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
@@ -219,12 +242,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int sub = (warp - 2) / 4;           // which of the quarter's warps
+    const bool owner = (lane / kRowsPerWarp) == sub;  // this lane's row is selected by this warp
     const int row_in_tile = quarter * 32 + lane;
     uint64_t* warp_lists = a.lists + (size_t(blockIdx.x) * kTileM + size_t(quarter) * 32) * CAP;
-    uint64_t* my_list = warp_lists + size_t(lane) * CAP;
+    float* stage = bars->stage[warp - 2];
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
+    const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t tcount = 0;
     for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       const int64_t qt = item % a.n_qtiles, sp = item / a.n_qtiles;
@@ -234,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t grow = m0 + row_in_tile;
       RowState st;
       st.cnt = 0;
-      st.tau = (grow < a.B) ? neg_inf : pos_inf;
+      st.tau = (owner && grow < a.B) ? neg_inf : pos_inf;
       for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
         const uint32_t buf = tcount & 1u, aphase = (tcount >> 1) & 1u;
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[buf]), aphase, a.diag, 6);
@@ -243,14 +269,19 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           float s[32];
-          ptx::tmem_ld32(taddr + c0, s);
+          if (DEBUG && (a.flags & 2)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[j] = neg_inf;
+          } else {
+            ptx::tmem_ld32(taddr + c0, s);
+          }
           if (c0 + 32 == BLOCK_N) {
             // all of this warp's TMEM reads of the buffer are done: hand it back
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[buf]));
           }
-          if (a.dump != nullptr && grow < a.B) {
+          if (DEBUG && a.dump != nullptr && owner && grow < a.B) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int64_t gn = n0 + c0 + j;
@@ -261,16 +292,30 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
           const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          if (mx > st.tau) {
-            uint32_t c = st.cnt;
+          unsigned hits = __ballot_sync(kFull, mx > st.tau);
+          if (DEBUG && (a.flags & 1)) hits = 0;
+          if (hits == 0) continue;
+          // ---- some row of this warp has a candidate in this chunk (about half the chunks)
+          const int64_t gn = n0 + c0 + lane;
+          const bool col_ok = gn < n_end;
+          const uint32_t gidx = uint32_t(gn + a.idx_offset);
+          while (hits) {
+            const int r = __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (lane == r) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (s[j] > st.tau) {
-                const int64_t gn = n0 + c0 + j;
-                if (gn < n_end) my_list[c++] = make_key(s[j], uint32_t(gn + a.idx_offset));
-              }
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(&stage[j]) = make_float4(s[j], s[j + 1], s[j + 2], s[j + 3]);
             }
-            st.cnt = c;
+            __syncwarp();
+            const float v = stage[lane];
+            const float tr = __shfl_sync(kFull, st.tau, r);
+            const uint32_t cr = __shfl_sync(kFull, st.cnt, r);
+            const bool p = (v > tr) && col_ok;
+            const unsigned pm = __ballot_sync(kFull, p);
+            if (p) warp_lists[size_t(r) * CAP + cr + __popc(pm & lt_mask)] = make_key(v, gidx);
+            if (lane == r) st.cnt += __popc(pm);
+            __syncwarp();
           }
           warp_maintain<ITEMS, 32>(warp_lists, st, a.k, lane);
         }
@@ -282,6 +327,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int64_t nv = a.B - row0;
         valid = nv >= 32 ? kFull : ((1u << nv) - 1u);
       }
+      valid &= (sub == 0) ? 0x0000FFFFu : 0xFFFF0000u;
+      static_assert(kEpiPerQuarter == 2, "row ownership masks assume two warps per quarter");
       uint64_t* out = a.out + (size_t(sp) * a.B + row0) * a.k;
       warp_flush<ITEMS>(warp_lists, st, a.k, lane, out, size_t(a.k), valid);
     }
@@ -331,9 +378,9 @@ bool make_map(CUtensorMap* m, const void* base, bool bf16, uint64_t rows, uint64
   return r == CUDA_SUCCESS;
 }
 
-template <int MODE, int BLOCK_N, int ITEMS>
+template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG>
 cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* dump, int32_t* diag,
-                     const char** why) {
+                     int flags, const char** why) {
   constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);
   const int d_pad = (p.D + 63) / 64 * 64;
   const int elems_per_row = kBf16 ? 64 : 32;
@@ -350,6 +397,7 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   a.out = p.out;
   a.dump = dump;
   a.diag = diag;
+  a.flags = flags;
   const int b_block = BLOCK_N * kRowBytes;
   const int stage_bytes = kBf16 ? b_block : 2 * (kABlockBytes + b_block);
   const int q_bytes = kBf16 ? a.n_kblocks * kABlockBytes : 0;
@@ -377,45 +425,48 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
     mq_lo = mq_hi;
     mb_lo = mb_hi;
   }
-  auto kern = tc_topk_kernel<MODE, BLOCK_N, ITEMS>;
+  auto kern = tc_topk_kernel<MODE, BLOCK_N, ITEMS, DEBUG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   kern<<<grid, kThreads, smem, stream>>>(mq_hi, mq_lo, mb_hi, mb_lo, a);
   return cudaGetLastError();
 }
 
-template <int MODE, int BLOCK_N>
+template <int MODE, int BLOCK_N, bool DEBUG>
 cudaError_t launch_cap(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
-                       int32_t* diag, const char** why) {
+                       int32_t* diag, int flags, const char** why) {
   switch (cap) {
-    case 64: return launch_t<MODE, BLOCK_N, 2>(p, grid, stream, dump, diag, why);
-    case 128: return launch_t<MODE, BLOCK_N, 4>(p, grid, stream, dump, diag, why);
-    case 256: return launch_t<MODE, BLOCK_N, 8>(p, grid, stream, dump, diag, why);
-    case 512: return launch_t<MODE, BLOCK_N, 16>(p, grid, stream, dump, diag, why);
-    case 1024: return launch_t<MODE, BLOCK_N, 32>(p, grid, stream, dump, diag, why);
+    case 64: return launch_t<MODE, BLOCK_N, 2, DEBUG>(p, grid, stream, dump, diag, flags, why);
+    case 128: return launch_t<MODE, BLOCK_N, 4, DEBUG>(p, grid, stream, dump, diag, flags, why);
+    case 256: return launch_t<MODE, BLOCK_N, 8, DEBUG>(p, grid, stream, dump, diag, flags, why);
+    case 512: return launch_t<MODE, BLOCK_N, 16, DEBUG>(p, grid, stream, dump, diag, flags, why);
+    case 1024: return launch_t<MODE, BLOCK_N, 32, DEBUG>(p, grid, stream, dump, diag, flags, why);
     default: *why = "unsupported k"; return cudaErrorNotSupported;
   }
 }
 
-}  // namespace
-
-int tc_tile_n(int mode, int dim) {
-  if (mode == B200KNN_MODE_BF16) return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
-  return 128;
-}
-
-cudaError_t launch_tc(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
-                      int32_t* diag, const char** why) {
-  *why = "";
+template <bool DEBUG>
+cudaError_t launch_mode(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
+                        int32_t* diag, int flags, const char** why) {
   if (p.mode == B200KNN_MODE_BF16) {
     if (tc_tile_n(p.mode, p.D) == 256)
-      return launch_cap<B200KNN_MODE_BF16, 256>(p, grid, cap, stream, dump, diag, why);
-    return launch_cap<B200KNN_MODE_BF16, 128>(p, grid, cap, stream, dump, diag, why);
+      return launch_cap<B200KNN_MODE_BF16, 256, DEBUG>(p, grid, cap, stream, dump, diag, flags, why);
+    return launch_cap<B200KNN_MODE_BF16, 128, DEBUG>(p, grid, cap, stream, dump, diag, flags, why);
   }
   if (p.mode == B200KNN_MODE_TF32X3)
-    return launch_cap<B200KNN_MODE_TF32X3, 128>(p, grid, cap, stream, dump, diag, why);
+    return launch_cap<B200KNN_MODE_TF32X3, 128, DEBUG>(p, grid, cap, stream, dump, diag, flags, why);
   *why = "unknown mode";
   return cudaErrorNotSupported;
+}
+
+}  // namespace
+
+cudaError_t launch_tc(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
+                      int32_t* diag, int flags, const char** why) {
+  *why = "";
+  // the debug instantiation (dump / experiment flags) is only reachable from the test hook
+  if (dump != nullptr || flags != 0) return launch_mode<true>(p, grid, cap, stream, dump, diag, flags, why);
+  return launch_mode<false>(p, grid, cap, stream, dump, diag, flags, why);
 }
 
 }  // namespace b200knn

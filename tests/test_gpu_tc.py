@@ -38,7 +38,7 @@ def run_dump(q: np.ndarray, bank_dn: np.ndarray, k: int, mode: str):
     rc = lib.b200knn_debug_topk_dump(_lib.MODES[mode], pq.hi.data_ptr(), None if pq.lo is None else pq.lo.data_ptr(),
                                      pb.hi.data_ptr(), None if pb.lo is None else pb.lo.data_ptr(),
                                      B, N, D, k, keys.data_ptr(), ws.data_ptr(), ws_bytes, dump.data_ptr(),
-                                     diag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                                     diag.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "debug_topk_dump")
     torch.cuda.synchronize()
     assert diag.cpu().tolist()[0] == 0, f"pipeline wait timed out: {diag.cpu().tolist()}"
