@@ -215,7 +215,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if mode != "exact":
-        K.bank_cache.get(bank, mode)
+        pbank = K.bank_cache.get(bank, K.RESCORED_MODES[mode]["cand"] if mode in K.RESCORED_MODES else mode)
+        if mode in K.RESCORED_MODES:
+            pbank.max_norm()
     e1.record()
     torch.cuda.synchronize()
     prepare_ms = e0.elapsed_time(e1)
@@ -269,16 +271,18 @@ def main():
         kern = sum(kern_ms) / max(1, len(kern_ms))
         flops = 2.0 * Q * n_local * DIM  # algorithmic: 2*N*D per query, this rank's rows
         achieved = flops / (kern * 1e-3) / 1e12
-        plan = b200knn.plan_info(Q, n_local, DIM, KNN_K, mode)
-        if mode == "bf16":
+        cand_mode = K.RESCORED_MODES[mode]["cand"] if mode in K.RESCORED_MODES else mode
+        k_plan = KNN_K + (K.RESCORED_MODES[mode]["margin"] if mode in K.RESCORED_MODES else 0)
+        plan = b200knn.plan_info(Q, n_local, DIM, k_plan, cand_mode)
+        if mode in ("bf16", "fp32_bf16"):
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                     "frac": achieved / pk["bf16"], "traffic": None,
                     "kernel": "tc_topk_kernel<BF16,256> (+ split-merge when splits>1)",
                     "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_ms": kern}
-        elif mode == "tf32x3":
+        elif mode in ("tf32x3", "fp32"):
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"] / 2, "unit": "TFLOP/s",
                     "frac": achieved / (pk["bf16"] / 2), "executed_frac": 3 * achieved / (pk["bf16"] / 2),
-                    "traffic": None, "kernel": "tc_topk_kernel<TF32X3,128>",
+                    "traffic": None, "kernel": "tc_topk_kernel<TF32X3,128>" + (" (candidates; + rescore_kernel)" if mode == "fp32" else ""),
                     "peak_source": f"{pk['src']} bf16 sustained / 2 (tf32 runs at half the bf16 rate)",
                     "kernel_ms": kern}
         else:
@@ -287,16 +291,16 @@ def main():
                     "frac": achieved / fp32_peak, "traffic": None, "kernel": "exact_topk_kernel",
                     "peak_source": "nominal 148 SM x 128 FMA/clk x 1.965 GHz", "kernel_ms": kern}
         launches_per_step = (0 if mode == "exact" else 1) + 1 + (1 if plan["splits"] > 1 else 0) + 1 \
-            + (1 if world > 1 else 0)
+            + (1 if world > 1 else 0) + (1 if mode in K.RESCORED_MODES else 0)
         line = {
             "metric": "kNN queries/s @811k×512 bank, k=200", "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "exact": "f32"}[mode], "data": "synthetic",
+            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "exact": "f32", "fp32": "tf32x3+f32", "fp32_bf16": "bf16+f32"}[mode], "data": "synthetic",
             "config": {"workload": f"knn_predict N={N} D={DIM} k={KNN_K} t={KNN_T} C={N_CLASSES}; "
                                    f"Q={Q} queries per step (clustered synthetic, WM-811K class priors)",
                        "mode": mode, "bank_sharding": f"row-sharded over {world} GPU(s)" if world > 1 else "none",
-                       "l2": "inputs larger than L2 (prepared bank %.0f MB)" % (n_local * DIM * (2 if mode == "bf16" else 8 if mode == "tf32x3" else 4) / 1e6),
+                       "l2": "inputs larger than L2 (prepared bank %.0f MB)" % (n_local * DIM * (2 if mode == "bf16" else 8 if mode in ("tf32x3", "fp32") else 4) / 1e6),
                        "plan": plan, "bank_prepare_ms_excluded": prepare_ms},
             "roofline": roof,
             "e2e": {"value": Q / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",
@@ -305,6 +309,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(),
         }
+        if mode in K.RESCORED_MODES:
+            line["config"]["uncertified_rows_last_step"] = K.last_rescore_stats["uncertified"]
         if world == 1 and not args.no_cpu_baseline:
             rate, times, threads = cpu_reference_rate(256, 8)
             line["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": threads, "kind": "port",

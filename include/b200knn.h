@@ -55,6 +55,7 @@ extern "C" {
 #define B200KNN_MODE_EXACT 0 /* CUDA-core fp32, sim = sequential fmaf over d (the on-device golden) */
 #define B200KNN_MODE_BF16 1  /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulate */
 #define B200KNN_MODE_TF32X3 2 /* tcgen05 kind::tf32, hi/lo split operands, 3 MMAs per k-step */
+#define B200KNN_MODE_F32ROWS 3 /* b200knn_prepare_rows only: plain fp32 (n_vec, dim_pad) row-major copy */
 
 int b200knn_version(void);
 const char* b200knn_last_error(void);
@@ -128,6 +129,32 @@ int b200knn_decode_keys(const uint64_t* keys, int64_t n_keys, float* sims,
 int b200knn_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
                  int64_t n_labels, int64_t label_offset, int C, double t,
                  int64_t* pred, double* scores, int32_t* err_flag, void* stream);
+
+/*
+ * Exact re-scoring of tensor-core candidates (the "fp32" mode; no counterpart in
+ * the reference — it is what makes the tensor-core contraction reproduce the
+ * fp32 torch.mm + topk of lightly's knn_predict bit for bit).
+ *   q        : caller queries (B, dim), q_dtype, row-major, ld = q_ld
+ *   rows_a/b : (N, dim_pad) fp32 bank rows from b200knn_prepare_rows (F32ROWS: rows_b
+ *              NULL; TF32X3: value = hi + lo, exact)
+ *   cand_keys: (B, k_in) keys from b200knn_topk (approximate sims), k_in <= 1024
+ *   out_keys : (B, k_out) keys with EXACT sims = fmaf chain over d (MODE_EXACT's
+ *              definition), canonical order
+ *   uncertified[b] = 1 when  exact_sim(rank k_out) <= approx_sim(rank k_in) + E,
+ *              E = err_coef * ||q_b|| * (*bank_max_norm)  — the candidate set is
+ *              then not proven to contain the true top-k and the caller must
+ *              recompute row b in MODE_EXACT; *n_uncertified counts such rows
+ *              (caller zeroes it).
+ * b200knn_row_norm_max writes max_n ||row_n|| (x1.001) to *out_dev.
+ */
+int b200knn_row_norm_max(const float* rows_a, const float* rows_b, int64_t n,
+                         int dim_pad, float* out_dev, void* stream);
+int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_a,
+                    const float* rows_b, int64_t N, int dim,
+                    const uint64_t* cand_keys, int64_t B, int k_in, int k_out,
+                    int64_t idx_offset, float err_coef, const float* bank_max_norm,
+                    uint64_t* out_keys, int32_t* uncertified,
+                    int32_t* n_uncertified, void* stream);
 
 /* Device capability probe for the host shim: 1 if the current device is sm_100. */
 int b200knn_device_ok(void);

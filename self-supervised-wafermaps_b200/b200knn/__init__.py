@@ -10,6 +10,8 @@ Public surface (mirrors the reference names for this path):
 """
 from .install import install, uninstall  # noqa: F401
 from .knn import (  # noqa: F401
+    ALL_MODES,
+    RESCORED_MODES,
     bank_cache,
     decode_keys,
     get_default_mode,

@@ -17,7 +17,7 @@ _DEFAULT = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb200knn.so"))
 # mirrors of the #defines in include/b200knn.h
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_DN, LAYOUT_ND = 0, 1
-MODE_EXACT, MODE_BF16, MODE_TF32X3 = 0, 1, 2
+MODE_EXACT, MODE_BF16, MODE_TF32X3, MODE_F32ROWS = 0, 1, 2, 3
 MODES = {"exact": MODE_EXACT, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3}
 
 # every symbol include/b200knn.h declares: (restype, argtypes)
@@ -41,6 +41,12 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p,
          c_void_p, c_void_p],
+    ),
+    "b200knn_row_norm_max": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "b200knn_rescore": (
+        c_int,
+        [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
+         c_int64, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "b200knn_plan_info": (c_int, [c_int, c_int64, c_int64, c_int, c_int, ctypes.POINTER(c_int64)]),
     "b200knn_debug_topk_dump": (

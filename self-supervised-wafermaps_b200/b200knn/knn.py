@@ -31,23 +31,41 @@ from . import _lib
 
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
-_default_mode = os.environ.get("B200KNN_MODE", "exact")
+_default_mode = os.environ.get("B200KNN_MODE", "fp32")
 
 # Measurement hook (bench.py): when set to a list, every b200knn_topk C call is bracketed by
 # CUDA events recorded on the launching stream and the (start, end) pair is appended.
 profile_events = None
 
 
+# "fp32" modes: tensor-core candidate generation + exact re-scoring (csrc/rescore.cu).
+#   candidate mode, extra candidates kept beyond k, error coefficient of the certificate
+#   (|approx - exact| <= coef * ||q|| * max||bank row||):
+#   tf32x3: 2e-5 is ~10x the largest error observed (dropped lo*lo terms 2^-21, fp32 TMEM
+#           accumulation);  bf16: 2^-8 is the rigorous Cauchy-Schwarz bound of two bf16 roundings.
+RESCORED_MODES = {
+    "fp32": dict(cand="tf32x3", margin=8, err_coef=2e-5),
+    "fp32_bf16": dict(cand="bf16", margin=40, err_coef=2.0 ** -8),
+}
+ALL_MODES = tuple(_lib.MODES) + tuple(RESCORED_MODES)
+
+# statistics of the last rescored call (bench / tests): rows that failed the certificate
+last_rescore_stats = {"rows": 0, "uncertified": 0}
+
+
 def set_default_mode(mode: str) -> None:
     """Select the similarity mode ``knn_predict``/``knn_topk`` use when none is passed.
 
-    ``"exact"``  fp32 CUDA-core contraction, sequential-fma similarities (bitwise reproducible);
-    ``"tf32x3"`` tcgen05 hi/lo-split TF32, fp32-class accuracy;
-    ``"bf16"``   tcgen05 BF16 operands / fp32 accumulate (fastest; recall@k reported by bench).
+    ``"exact"``     fp32 CUDA-core contraction, sequential-fma similarities (bitwise reproducible);
+    ``"fp32"``      tcgen05 3xTF32 candidates + exact re-scoring + certificate: bitwise the
+                    ``"exact"`` result at tensor-core speed (the fp32-matching mode);
+    ``"fp32_bf16"`` same with BF16 candidates (fastest exact mode when neighbours are well separated);
+    ``"tf32x3"``    raw tcgen05 hi/lo-split TF32 similarities (fp32-class accuracy, ~1e-6);
+    ``"bf16"``      raw tcgen05 BF16 operands / fp32 accumulate (fastest; recall@k reported by bench).
     """
     global _default_mode
-    if mode not in _lib.MODES:
-        raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(_lib.MODES)}")
+    if mode not in ALL_MODES:
+        raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(ALL_MODES)}")
     _default_mode = mode
 
 
@@ -84,10 +102,32 @@ def padded_dim(dim: int) -> int:
 class PreparedRows:
     """K-major rows in the layout the tensor-core kernel streams with TMA."""
 
-    __slots__ = ("mode", "n", "dim", "hi", "lo")
+    __slots__ = ("mode", "n", "dim", "hi", "lo", "_f32", "_max_norm", "_src")
 
     def __init__(self, mode: str, n: int, dim: int, hi: torch.Tensor, lo: Optional[torch.Tensor]):
         self.mode, self.n, self.dim, self.hi, self.lo = mode, n, dim, hi, lo
+        self._f32 = None       # (n, dim_pad) fp32 shadow rows for the exact re-scoring (bf16 candidates)
+        self._max_norm = None  # device scalar: max row norm (certificate)
+        self._src = None       # (tensor, vectors_are_columns) to build the shadow lazily
+
+    def rescore_rows(self):
+        """(rows_a, rows_b) fp32 row-major operands whose sum is the caller's exact value."""
+        if self.mode == "tf32x3":
+            return self.hi, self.lo
+        if self._f32 is None:
+            src, cols = self._src
+            self._f32 = prepare_rows(src, "f32rows", cols).hi
+        return self._f32, None
+
+    def max_norm(self) -> torch.Tensor:
+        if self._max_norm is None:
+            a, b = self.rescore_rows()
+            out = torch.zeros((1,), dtype=torch.float32, device=a.device)
+            with torch.cuda.device(a.device):
+                _lib.check(_lib.load().b200knn_row_norm_max(a.data_ptr(), _ptr(b), self.n, a.shape[1],
+                                                            out.data_ptr(), _stream()), "row_norm_max")
+            self._max_norm = out
+        return self._max_norm
 
 
 def _layout_of(x: torch.Tensor, vectors_are_columns: bool) -> Tuple[torch.Tensor, int, int]:
@@ -121,15 +161,22 @@ def prepare_rows(x: torch.Tensor, mode: str, vectors_are_columns: bool) -> Prepa
     elif mode == "tf32x3":
         hi = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
         lo = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
+    elif mode == "f32rows":
+        hi = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
+        lo = None
     else:
         raise ValueError(f"mode {mode!r} takes caller tensors directly")
+    code = _lib.MODE_F32ROWS if mode == "f32rows" else _lib.MODES[mode]
     if n > 0:
-        _lib.check(
-            lib.b200knn_prepare_rows(x.data_ptr(), _DTYPES[x.dtype], layout, n, dim, ld,
-                                     _lib.MODES[mode], hi.data_ptr(), _ptr(lo), _stream()),
-            "prepare_rows",
-        )
-    return PreparedRows(mode, n, dim, hi, lo)
+        with torch.cuda.device(x.device):
+            _lib.check(
+                lib.b200knn_prepare_rows(x.data_ptr(), _DTYPES[x.dtype], layout, n, dim, ld,
+                                         code, hi.data_ptr(), _ptr(lo), _stream()),
+                "prepare_rows",
+            )
+    prep = PreparedRows(mode, n, dim, hi, lo)
+    prep._src = (x, vectors_are_columns)
+    return prep
 
 
 class _BankCache:
@@ -189,6 +236,8 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
     the canonical (sim desc, bank index asc) order; bank indices are offset by idx_offset."""
     lib = _lib.load()
     mode = mode or _default_mode
+    if mode in RESCORED_MODES:
+        return _topk_keys_rescored(feature, feature_bank, k, mode, idx_offset)
     if mode not in _lib.MODES:
         raise ValueError(f"unknown mode {mode!r}")
     _check_feature_bank(feature, feature_bank)
@@ -233,6 +282,47 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
             profile_events.append(ev)
         _lib.check(rc, "topk")
     return keys
+
+
+def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
+                        idx_offset: int = 0) -> torch.Tensor:
+    """Tensor-core candidates (k_in = k + margin) -> exact sequential-fma re-scoring -> best k,
+    with a per-row certificate; uncertified rows are recomputed in "exact" mode, so the keys are
+    bitwise those of mode "exact"."""
+    lib = _lib.load()
+    cfg = RESCORED_MODES[mode]
+    _check_feature_bank(feature, feature_bank)
+    B, D = feature.shape
+    N = feature_bank.shape[1]
+    k = int(k)
+    if k <= 0 or k > N:
+        raise RuntimeError("selected index k out of range")
+    k_in = min(N, k + cfg["margin"])
+    dev = feature.device
+    out = torch.empty((B, k), dtype=torch.int64, device=dev)
+    if B == 0:
+        return out
+    cand = topk_keys(feature, feature_bank, k_in, cfg["cand"], idx_offset)
+    pb = bank_cache.get(feature_bank, cfg["cand"])
+    rows_a, rows_b = pb.rescore_rows()
+    max_norm = pb.max_norm()
+    q = feature if feature.dtype in _DTYPES else feature.float()
+    if q.stride(1) != 1:
+        q = q.contiguous()
+    with torch.cuda.device(dev):
+        flags = torch.empty((B,), dtype=torch.int32, device=dev)
+        n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(lib.b200knn_rescore(q.data_ptr(), _DTYPES[q.dtype], q.stride(0), rows_a.data_ptr(),
+                                       _ptr(rows_b), N, D, cand.data_ptr(), B, k_in, k, idx_offset,
+                                       float(cfg["err_coef"]), max_norm.data_ptr(), out.data_ptr(),
+                                       flags.data_ptr(), n_bad.data_ptr(), _stream()), "rescore")
+        bad = int(n_bad.item())
+        last_rescore_stats["rows"] = B
+        last_rescore_stats["uncertified"] = bad
+        if bad:
+            rows = flags.nonzero(as_tuple=False).view(-1)
+            out[rows] = topk_keys(q[rows].contiguous(), feature_bank, k, "exact", idx_offset)
+    return out
 
 
 def decode_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -63,8 +63,8 @@ int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout, int64_t
     return fail(B200KNN_E_ARG, "prepare_rows: unknown dtype");
   if (src_layout != B200KNN_LAYOUT_DN && src_layout != B200KNN_LAYOUT_ND)
     return fail(B200KNN_E_ARG, "prepare_rows: unknown layout");
-  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3)
-    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16 or TF32X3");
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_F32ROWS)
+    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16, TF32X3 or F32ROWS");
   if (mode == B200KNN_MODE_TF32X3 && !dst_lo)
     return fail(B200KNN_E_ARG, "prepare_rows: TF32X3 needs dst_lo");
   cudaError_t e = b200knn::launch_prepare(src, src_dtype, src_layout, n_vec, dim, ld, mode, dst_hi,
@@ -206,6 +206,45 @@ int b200knn_merge(const uint64_t* keys_in, int G, int64_t B, int k_in, int k_out
   cudaError_t e = b200knn::launch_merge(keys_in, G, B, k_in, k_out, keys_out,
                                         static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? B200KNN_OK : fail_cuda("merge", e);
+}
+
+int b200knn_row_norm_max(const float* rows_a, const float* rows_b, int64_t n, int dim_pad,
+                         float* out_dev, void* stream) {
+  if (!rows_a || !out_dev || n < 0 || dim_pad <= 0) return fail(B200KNN_E_ARG, "row_norm_max: bad argument");
+  cudaError_t e = b200knn::launch_row_norm_max(rows_a, rows_b, n, dim_pad, out_dev,
+                                               static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("row_norm_max", e);
+}
+
+int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_a, const float* rows_b,
+                    int64_t N, int dim, const uint64_t* cand_keys, int64_t B, int k_in, int k_out,
+                    int64_t idx_offset, float err_coef, const float* bank_max_norm,
+                    uint64_t* out_keys, int32_t* uncertified, int32_t* n_uncertified, void* stream) {
+  if (!q || !rows_a || !cand_keys || !bank_max_norm || !out_keys || !uncertified || !n_uncertified)
+    return fail(B200KNN_E_ARG, "rescore: null pointer");
+  if (B < 0 || N <= 0 || dim <= 0 || k_out <= 0 || k_in < k_out || k_in > 1024)
+    return fail(B200KNN_E_ARG, "rescore: bad shape (need 0 < k_out <= k_in <= 1024)");
+  if (q_dtype < 0 || q_dtype > 2) return fail(B200KNN_E_ARG, "rescore: unknown dtype");
+  b200knn::RescoreParams p;
+  p.q = q;
+  p.q_dtype = q_dtype;
+  p.q_ld = q_ld;
+  p.rows_a = rows_a;
+  p.rows_b = rows_b;
+  p.dim = dim;
+  p.dim_pad = (dim + 63) / 64 * 64;
+  p.cand = cand_keys;
+  p.B = B;
+  p.k_in = k_in;
+  p.k_out = k_out;
+  p.idx_offset = idx_offset;
+  p.err_coef = err_coef;
+  p.bank_max_norm = bank_max_norm;
+  p.out = out_keys;
+  p.uncertified = uncertified;
+  p.n_uncertified = n_uncertified;
+  cudaError_t e = b200knn::launch_rescore(p, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("rescore", e);
 }
 
 int b200knn_decode_keys(const uint64_t* keys, int64_t n_keys, float* sims, int64_t* idx, void* stream) {

@@ -131,10 +131,14 @@ struct RowState {
 // After a chunk of at most CHUNK appends per row: prune every row of the warp
 // whose list could overflow during the next chunk.  `lists` points at the
 // warp's first row; row r of the warp is lane r.
-template <int ITEMS, int CHUNK>
-__device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int k, int lane) {
+// slack = free slots every row must keep: the hard bound is the most a row can
+// append before the next call (32 per chunk); callers that run off the critical
+// path pass a larger value to prune early, where it stalls nobody.
+template <int ITEMS>
+__device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int k, int lane,
+                                              int slack) {
   constexpr int CAP = ITEMS * 32;
-  const bool need = (st.cnt + CHUNK > CAP);
+  const bool need = (int(st.cnt) + slack > CAP) && (int(st.cnt) > k);
   unsigned m = __ballot_sync(kFull, need);
   if (m == 0) return;
   __syncwarp();  // owner's appends visible to the whole warp

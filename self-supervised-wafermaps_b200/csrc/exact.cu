@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(ExactParams p) {
             }
           }
           st.cnt = c;
-          warp_maintain<ITEMS, 32>(warp_lists, st, p.k, lane);
+          warp_maintain<ITEMS>(warp_lists, st, p.k, lane, 32);
         }
       }
       __syncthreads();

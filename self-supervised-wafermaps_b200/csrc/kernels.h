@@ -35,6 +35,28 @@ cudaError_t launch_vote(const uint64_t* keys, const int64_t* labels, int64_t B, 
 cudaError_t launch_prepare(const void* src, int src_dtype, int src_layout, int64_t n_vec, int dim,
                            int64_t ld, int mode, void* dst_hi, void* dst_lo, cudaStream_t stream);
 
+// exact re-scoring of tensor-core candidates (rescore.cu)
+struct RescoreParams {
+  const void* q;        // caller queries (B, dim), row-major, ld = q_ld
+  int q_dtype;
+  int64_t q_ld;
+  const float* rows_a;  // (N, dim_pad) fp32 bank rows; value = rows_a + rows_b when rows_b != nullptr
+  const float* rows_b;
+  int dim, dim_pad;
+  const uint64_t* cand;  // (B, k_in) candidate keys, sorted descending under the approximate sims
+  int64_t B;
+  int k_in, k_out;
+  int64_t idx_offset;
+  float err_coef;
+  const float* bank_max_norm;  // device scalar
+  uint64_t* out;               // (B, k_out)
+  int32_t* uncertified;        // (B,)
+  int32_t* n_uncertified;      // device counter (caller zeroes)
+};
+cudaError_t launch_rescore(const RescoreParams& p, cudaStream_t stream);
+cudaError_t launch_row_norm_max(const float* a, const float* b, int64_t n, int dim_pad, float* out,
+                                cudaStream_t stream);
+
 // tensor-core path (tc_topk.cu)
 struct TcParams {
   int mode;  // B200KNN_MODE_BF16 / TF32X3

@@ -49,7 +49,10 @@ constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kRowBytes = 128;                   // one swizzle row = one k-block of a vector
 constexpr int kABlockBytes = kTileM * kRowBytes;  // 16 KB: 128 query rows x one k-block
-constexpr int kEpiPerQuarter = 2;  // epilogue warps per TMEM lane quarter
+#ifndef B200KNN_EPI_PER_QUARTER
+#define B200KNN_EPI_PER_QUARTER 2
+#endif
+constexpr int kEpiPerQuarter = B200KNN_EPI_PER_QUARTER;  // epilogue warps per TMEM lane quarter
 constexpr int kEpiWarps = 4 * kEpiPerQuarter;
 constexpr int kRowsPerWarp = 32 / kEpiPerQuarter;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -247,10 +250,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const bool owner = (lane / kRowsPerWarp) == sub;  // this lane's row is selected by this warp
     const int row_in_tile = quarter * 32 + lane;
     uint64_t* warp_lists = a.lists + (size_t(blockIdx.x) * kTileM + size_t(quarter) * 32) * CAP;
-    float* stage = bars->stage[warp - 2];
+    const uint32_t stage = ptx::smem_u32(bars->stage[warp - 2]);
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
     const unsigned lt_mask = (1u << lane) - 1u;
+    // free slots below which a row is pruned between tiles (off the critical path)
+    const int soft_slack = min(96, (CAP - a.k) / 2);
     uint32_t tcount = 0;
     for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       const int64_t qt = item % a.n_qtiles, sp = item / a.n_qtiles;
@@ -305,10 +310,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (lane == r) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(&stage[j]) = make_float4(s[j], s[j + 1], s[j + 2], s[j + 3]);
+                ptx::st_shared_v4(stage + j * 4, s[j], s[j + 1], s[j + 2], s[j + 3]);
             }
             __syncwarp();
-            const float v = stage[lane];
+            const float v = ptx::ld_shared_f32(stage + lane * 4);
             const float tr = __shfl_sync(kFull, st.tau, r);
             const uint32_t cr = __shfl_sync(kFull, st.cnt, r);
             const bool p = (v > tr) && col_ok;
@@ -317,8 +322,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (lane == r) st.cnt += __popc(pm);
             __syncwarp();
           }
-          warp_maintain<ITEMS, 32>(warp_lists, st, a.k, lane);
+          warp_maintain<ITEMS>(warp_lists, st, a.k, lane, 32);  // emergency only (list would overflow)
         }
+        // The TMEM buffer went back to the MMA warp before the last chunk was processed:
+        // prune here, off the accumulator's critical path, a little before it becomes mandatory.
+        warp_maintain<ITEMS>(warp_lists, st, a.k, lane, soft_slack);
         ++tcount;
       }
       const int64_t row0 = m0 + quarter * 32;
@@ -327,8 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int64_t nv = a.B - row0;
         valid = nv >= 32 ? kFull : ((1u << nv) - 1u);
       }
-      valid &= (sub == 0) ? 0x0000FFFFu : 0xFFFF0000u;
-      static_assert(kEpiPerQuarter == 2, "row ownership masks assume two warps per quarter");
+      valid &= (kRowsPerWarp == 32 ? kFull : ((1u << kRowsPerWarp) - 1u)) << (sub * kRowsPerWarp);
       uint64_t* out = a.out + (size_t(sp) * a.B + row0) * a.k;
       warp_flush<ITEMS>(warp_lists, st, a.k, lane, out, size_t(a.k), valid);
     }

@@ -13,6 +13,7 @@ import torch
 import b200knn
 import datagen
 from b200knn import _lib
+from b200knn import knn as K
 from oracle import knn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -84,12 +85,65 @@ def test_tiles_and_selection(name, _, mode):
 
 
 @pytest.mark.parametrize("name", ["clustered_small", "gauss_small", "mixed38"])
-def test_tf32x3_meets_fp32_contract(name):
+def test_tf32x3_raw_accuracy(name):
+    """Raw 3xTF32 similarities: within 1e-5 relative of fp64 (north-star tolerance).  Their ORDER is
+    only guaranteed where fp64 neighbours differ by more than the mode's error (2e-5*max|s|: dropped
+    lo*lo terms and non-IEEE fp32 accumulation in TMEM) — bit-exact order is the job of mode "fp32"."""
     c = datagen.make_case(name)
     sims, idx = b200knn.knn_topk(_t(c["feature"]), _t(c["bank"]), c["k"], mode="tf32x3")
-    r = O.compare_topk(sims.cpu().numpy(), idx.cpu().numpy(), c["feature"], c["bank"], c["k"])
-    assert r["max_rel_err"] <= 1e-5
+    r = O.compare_topk(sims.cpu().numpy(), idx.cpu().numpy(), c["feature"], c["bank"], c["k"], eps_scale=2e-5)
+    print(f"tf32x3 {name}: max rel err {r['max_rel_err']:.2e}, idx mismatches {r['idx_mismatch_total']:.0f}")
+    assert r["max_rel_err"] <= 1e-5  # tolerance stated by BASELINE.json north_star
     assert r["idx_mismatch_unambiguous"] == 0 and r["set_mismatch_rows_unambiguous"] == 0
+    assert r["recall_at_k"] >= 0.999
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16"])
+@pytest.mark.parametrize("name", datagen.CASE_NAMES)
+def test_fp32_modes_bitwise_equal_exact_and_oracle(name, mode):
+    """The fp32-matching modes (tensor-core candidates + exact re-scoring + certificate) must give
+    bit for bit the neighbours, similarities and class ranking of the sequential-fma oracle."""
+    c = datagen.make_case(name)
+    f, bank, lab = _t(c["feature"]), _t(c["bank"]), _t(c["labels"])
+    keys = b200knn.topk_keys(f, bank, c["k"], mode=mode)
+    stats = dict(K.last_rescore_stats)
+    sims, idx = b200knn.decode_keys(keys)
+    ss, si = O.topk_seqfma(c["feature"], c["bank"], c["k"])
+    assert np.array_equal(idx.cpu().numpy(), si)
+    assert np.array_equal(sims.cpu().numpy().view(np.uint32), ss.view(np.uint32))
+    assert torch.equal(keys, b200knn.topk_keys(f, bank, c["k"], mode="exact"))
+    b200knn.set_default_mode(mode)
+    try:
+        pred = b200knn.knn_predict(f, bank, lab, c["C"], c["k"], c["t"]).cpu().numpy()
+    finally:
+        b200knn.set_default_mode("exact")
+    assert np.array_equal(pred, O.vote_o64(ss, si, c["labels"], c["C"], c["t"])[0])
+    print(f"{mode} {name}: uncertified rows {stats['uncertified']}/{stats['rows']}")
+    if mode == "fp32":
+        assert stats["uncertified"] <= max(1, stats["rows"] // 10)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16"])
+@pytest.mark.parametrize("model", ["FastSiam", "SimSiam"])
+def test_fp32_modes_real_banks(model, mode, golden_dir):
+    """Duplicates, 80 % exact zeros, row norms up to 277 (un-normalised): certificate + fallback
+    must still reproduce the golden sequential-fma result exactly."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, f"real_{model}.npz"))
+    for tag in ("norm_", "raw_"):
+        b = g["bank_rows_f16"].astype(np.float32)
+        q = g["query_rows_f16"].astype(np.float32)
+        if tag == "norm_":
+            b = b / np.maximum(np.linalg.norm(b, axis=1, keepdims=True), 1e-12)
+            q = q / np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-12)
+        bank = np.ascontiguousarray(b.T)
+        for k in (5, 200):
+            keys = b200knn.topk_keys(_t(q), _t(bank), k, mode=mode)
+            sims, idx = b200knn.decode_keys(keys)
+            assert np.array_equal(idx.cpu().numpy(), g[f"{tag}k{k}_seq_idx"].astype(np.int64)), (tag, k)
+            assert np.array_equal(sims.cpu().numpy().view(np.uint32), g[f"{tag}k{k}_seq_sims"].view(np.uint32))
+            print(f"{mode} {model} {tag}k{k}: uncertified {K.last_rescore_stats['uncertified']}/{K.last_rescore_stats['rows']}")
 
 
 @pytest.mark.parametrize("name", ["clustered_small", "gauss_small"])
@@ -101,7 +155,7 @@ def test_bf16_recall(name):
     assert r["recall_at_k"] >= 0.98 and r["max_rel_err"] <= 2e-2
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "fp32", "fp32_bf16"])
 def test_large_bank_against_exact_mode(mode):
     """Sizes the CPU oracle cannot cover: tensor-core modes against the on-device exact mode
     (itself bit-checked against the oracle in test_gpu_exact.py) on a 811,457 x 512 bank."""
@@ -109,15 +163,20 @@ def test_large_bank_against_exact_mode(mode):
     g = torch.Generator(device=DEV).manual_seed(811)
     bank = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device=DEV), dim=1).t().contiguous()
     q = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device=DEV), dim=1)
-    es, ei = b200knn.knn_topk(q, bank, k, mode="exact")
-    ts, ti = b200knn.knn_topk(q, bank, k, mode=mode)
+    ek = b200knn.topk_keys(q, bank, k, mode="exact")
+    tk = b200knn.topk_keys(q, bank, k, mode=mode)
+    es, ei = b200knn.decode_keys(ek)
+    ts, ti = b200knn.decode_keys(tk)
     ei, ti = ei.cpu().numpy(), ti.cpu().numpy()
     recall = np.mean([len(set(ei[b]) & set(ti[b])) / k for b in range(B)])
     print(f"{mode} recall@{k} vs exact at N={N}: {recall:.5f}")
-    if mode == "tf32x3":
+    if mode in ("fp32", "fp32_bf16"):
+        print(f"   uncertified rows {K.last_rescore_stats['uncertified']}/{K.last_rescore_stats['rows']}")
+        assert torch.equal(ek, tk)  # bitwise: indices, similarities, order
+    elif mode == "tf32x3":
         assert recall >= 0.9995 and float((es - ts).abs().max()) <= 1e-5
         # batch invariance of the tensor-core path: same rows, smaller batch, identical keys
-        ts2, ti2 = b200knn.knn_topk(q[:64].contiguous(), bank, k, mode=mode)
-        assert torch.equal(ts2, ts[:64]) and np.array_equal(ti2.cpu().numpy(), ti[:64])
+        tk2 = b200knn.topk_keys(q[:64].contiguous(), bank, k, mode=mode)
+        assert torch.equal(tk2, tk[:64])
     else:
         assert recall >= 0.98

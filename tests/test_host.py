@@ -41,7 +41,7 @@ def test_layout_detection():
 
 
 def test_modes():
-    assert b200knn.get_default_mode() in ("exact", "bf16", "tf32x3")
+    assert b200knn.get_default_mode() in b200knn.ALL_MODES
     with pytest.raises(ValueError):
         b200knn.set_default_mode("fp8")
     old = b200knn.get_default_mode()
