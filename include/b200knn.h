@@ -101,6 +101,25 @@ int b200knn_topk(int mode,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * b200knn_topk for the tensor-core modes with two extras used by the sampling
+ * pre-pass (no counterpart in the reference):
+ *   bank_row_stride: visit prepared bank rows 0, s, 2s, ... (n_visit of them);
+ *                    returned indices are the VISIT index (+ idx_offset)
+ *   tau0           : optional (B,) initial admission thresholds: only rows with
+ *                    sim > tau0[b] are considered, so fewer than k may be found
+ *                    (the remaining key slots are 0); NULL = no threshold.
+ * A threshold taken from the r-th best similarity of a strided sample is below
+ * the true k-th similarity except with negligible probability; the host shim
+ * detects the exception (empty k-th slot) and recomputes that row without tau0.
+ */
+int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo,
+                    const void* bank_hi, const void* bank_lo, int64_t B,
+                    int64_t n_visit, int dim, int k, int64_t idx_offset,
+                    int64_t bank_row_stride, const float* tau0,
+                    uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/*
  * Merge G sorted candidate lists per query into one (replaces nothing in the
  * reference; it is the exchange step of the bank-row-sharded mode, applied to
  * the buffer an all-gather of per-shard b200knn_topk outputs produces).

@@ -210,6 +210,28 @@ class _BankCache:
 bank_cache = _BankCache()
 
 
+class _QueryCache:
+    """The prepared copy of the last query batch (used twice per call: pre-pass and main pass)."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, feature: torch.Tensor, mode: str) -> PreparedRows:
+        key = (feature.data_ptr(), feature._version, tuple(feature.shape), tuple(feature.stride()),
+               feature.dtype, feature.device.index, mode)
+        if key != self._key or self._val is None or self._val[0]() is None:
+            prep = prepare_rows(feature, mode, vectors_are_columns=False)
+            self._key, self._val = key, (weakref.ref(feature), prep)
+        return self._val[1]
+
+    def clear(self) -> None:
+        self._key = self._val = None
+
+
+query_cache = _QueryCache()
+
+
 # ----------------------------------------------------------------------------
 # selection keys
 # ----------------------------------------------------------------------------
@@ -230,10 +252,75 @@ def _check_feature_bank(feature: torch.Tensor, feature_bank: torch.Tensor) -> No
         )
 
 
+# Sampling pre-pass (tensor-core modes): the r-th best similarity of every s-th bank row is,
+# except with probability P[Binomial(k, 1/s) >= r] (2e-7 for the defaults), below the true k-th
+# best, so it is a valid starting threshold for the streaming selection.  It removes the list
+# warm-up (the first ~k*ln(N/k) insertions), which is what a (query tile, bank shard) work item
+# otherwise pays as a fixed cost; rows where the bound fails end with an empty k-th slot and are
+# recomputed without it.
+PREPASS = {"enabled": os.environ.get("B200KNN_PREPASS", "1") == "1", "r": 16, "rank_factor": 5.0,
+           "min_k": 64, "min_sample_rows": 1024}
+
+
+def prepass_stride(n_rows: int, k: int) -> int:
+    """Row stride of the sampling pre-pass, or 0 when it does not pay (small k or small bank)."""
+    if not PREPASS["enabled"] or k < PREPASS["min_k"]:
+        return 0
+    s = max(8, min(256, int(round(PREPASS["rank_factor"] * k / PREPASS["r"]))))
+    return s if n_rows // s >= PREPASS["min_sample_rows"] else 0
+
+
+def _tc_call(mode, pq, pb, B, n_visit, D, k, idx_offset, stride, tau0, dev, timed=False):
+    lib = _lib.load()
+    keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+    ws_bytes = lib.b200knn_topk_workspace_bytes(B, n_visit, D, k, _lib.MODES[mode])
+    if ws_bytes == 0:
+        raise RuntimeError(f"b200knn: unsupported problem (B={B}, N={n_visit}, D={D}, k={k})")
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    ev = None
+    if timed and profile_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    rc = lib.b200knn_topk_ex(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(), _ptr(pb.lo),
+                             B, n_visit, D, k, idx_offset, stride, _ptr(tau0), keys.data_ptr(),
+                             ws.data_ptr(), ws_bytes, _stream())
+    if ev is not None:
+        ev[1].record()
+        profile_events.append(ev)
+    _lib.check(rc, "topk")
+    return keys
+
+
+def kth_sim(keys: torch.Tensor) -> torch.Tensor:
+    """Similarity of the last key of every row (-inf for an empty slot): a (B,) fp32 tensor."""
+    return decode_keys(keys[:, -1:].contiguous())[0].view(-1).contiguous()
+
+
+def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
+                n_rows_for_decision: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Pre-pass: (B, r) best keys among every s-th bank row, or None when the pre-pass is off."""
+    N = feature_bank.shape[1]
+    s = prepass_stride(n_rows_for_decision if n_rows_for_decision is not None else N, k)
+    if s == 0 or mode not in ("bf16", "tf32x3"):
+        return None
+    B, D = feature.shape
+    r = PREPASS["r"]
+    n_visit = (N + s - 1) // s
+    if n_visit < r:
+        return None
+    with torch.cuda.device(feature.device):
+        pb = bank_cache.get(feature_bank, mode)
+        pq = query_cache.get(feature, mode)
+        return _tc_call(mode, pq, pb, B, n_visit, D, r, 0, s, None, feature.device)
+
+
 def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: Optional[str] = None,
-              idx_offset: int = 0) -> torch.Tensor:
+              idx_offset: int = 0, tau0: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(B,k) selection keys (uint64 bit patterns in an int64 tensor), sorted descending under
-    the canonical (sim desc, bank index asc) order; bank indices are offset by idx_offset."""
+    the canonical (sim desc, bank index asc) order; bank indices are offset by idx_offset.
+
+    tau0 (tensor-core modes): caller-supplied (B,) admission thresholds — then no pre-pass and
+    no validation happen here and rows may come back with empty (0) slots (sharded driver)."""
     lib = _lib.load()
     mode = mode or _default_mode
     if mode in RESCORED_MODES:
@@ -248,40 +335,63 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
         raise RuntimeError("selected index k out of range")  # Tensor.topk's message
     dev = feature.device
     with torch.cuda.device(dev):
-        keys = torch.empty((B, k), dtype=torch.int64, device=dev)
         if B == 0:
-            return keys
-        ws_bytes = lib.b200knn_topk_workspace_bytes(B, N, D, k, _lib.MODES[mode])
-        if ws_bytes == 0:
-            raise RuntimeError(f"b200knn: unsupported problem (B={B}, N={N}, D={D}, k={k})")
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        ev = None
-        if mode != "exact":
-            pb = bank_cache.get(feature_bank, mode)
-            pq = prepare_rows(feature, mode, vectors_are_columns=False)
-        if profile_events is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
+            return torch.empty((B, k), dtype=torch.int64, device=dev)
         if mode == "exact":
+            keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+            ws_bytes = lib.b200knn_topk_workspace_bytes(B, N, D, k, _lib.MODE_EXACT)
+            if ws_bytes == 0:
+                raise RuntimeError(f"b200knn: unsupported problem (B={B}, N={N}, D={D}, k={k})")
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
             q = feature if feature.dtype in _DTYPES else feature.float()
             if q.stride(1) != 1:
                 q = q.contiguous()
             bank = feature_bank if feature_bank.dtype in _DTYPES else feature_bank.float()
             bank, layout, ld = _layout_of(bank, vectors_are_columns=True)
+            ev = None
+            if profile_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             rc = lib.b200knn_topk(_lib.MODE_EXACT, q.data_ptr(), None, _DTYPES[q.dtype], q.stride(0),
                                   bank.data_ptr(), None, _DTYPES[bank.dtype], layout, ld,
                                   B, N, D, k, idx_offset, keys.data_ptr(), ws.data_ptr(), ws_bytes,
                                   _stream())
-        else:
-            rc = lib.b200knn_topk(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), 0, 0,
-                                  pb.hi.data_ptr(), _ptr(pb.lo), 0, 0, 0,
-                                  B, N, D, k, idx_offset, keys.data_ptr(), ws.data_ptr(), ws_bytes,
-                                  _stream())
-        if ev is not None:
-            ev[1].record()
-            profile_events.append(ev)
-        _lib.check(rc, "topk")
+            if ev is not None:
+                ev[1].record()
+                profile_events.append(ev)
+            _lib.check(rc, "topk")
+            return keys
+        pb = bank_cache.get(feature_bank, mode)
+        pq = query_cache.get(feature, mode)
+        if tau0 is not None:
+            return _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, tau0.contiguous(), dev, timed=True)
+        sk = sample_keys(feature, feature_bank, k, mode)
+        if sk is None:
+            return _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, None, dev, timed=True)
+        keys = _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, kth_sim(sk), dev, timed=True)
+        return _repair_rows(keys, lambda rows: _tc_call(mode, _rows_of(pq, rows), pb, rows.numel(), N, D, k,
+                                                        idx_offset, 1, None, dev))
+
+
+def _rows_of(pq: "PreparedRows", rows: torch.Tensor) -> "PreparedRows":
+    return PreparedRows(pq.mode, rows.numel(), pq.dim, pq.hi[rows].contiguous(),
+                        None if pq.lo is None else pq.lo[rows].contiguous())
+
+
+def _repair_rows(keys: torch.Tensor, recompute) -> torch.Tensor:
+    """Rows whose k-th slot is empty were selected under a threshold that was too high (the
+    ~1e-7 tail of the sampling pre-pass): recompute them without a threshold."""
+    bad = keys[:, -1] == 0
+    last_prepass_stats["rows"] = keys.shape[0]
+    n_bad = int(bad.sum().item())
+    last_prepass_stats["repaired"] = n_bad
+    if n_bad:
+        rows = bad.nonzero(as_tuple=False).view(-1)
+        keys[rows] = recompute(rows)
     return keys
+
+
+last_prepass_stats = {"rows": 0, "repaired": 0}
 
 
 def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,

@@ -33,9 +33,19 @@ class _CudaOps:
     """Default compute backend: the C-ABI CUDA library."""
 
     @staticmethod
-    def topk_keys(feature, bank_shard, k, mode, idx_offset):
+    def topk_keys(feature, bank_shard, k, mode, idx_offset, tau0=None):
         from .knn import topk_keys
-        return topk_keys(feature, bank_shard, k, mode, idx_offset)
+        return topk_keys(feature, bank_shard, k, mode, idx_offset, tau0)
+
+    @staticmethod
+    def sample_keys(feature, bank_shard, k, mode, n_rows_global):
+        from .knn import sample_keys
+        return sample_keys(feature, bank_shard, k, mode, n_rows_global)
+
+    @staticmethod
+    def kth_sim(keys):
+        from .knn import kth_sim
+        return kth_sim(keys)
 
     @staticmethod
     def merge_keys(keys_in, k_out):
@@ -85,26 +95,52 @@ class ShardedBank:
         lo, hi = shard_bounds(n, ws, rk)
         return cls(feature_bank[:, lo:hi].contiguous(), labels, n, **kw)
 
-    def local_keys(self, feature: torch.Tensor, k: int) -> torch.Tensor:
+    def local_keys(self, feature: torch.Tensor, k: int, tau0: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Per-shard top-min(k, shard rows) keys with GLOBAL indices, padded to k with empty keys."""
         rows = self.hi - self.lo
         k_loc = min(k, rows)
         B = feature.shape[0]
         keys = torch.zeros((B, k), dtype=torch.int64, device=feature.device)
         if k_loc > 0:
-            keys[:, :k_loc] = self.ops.topk_keys(feature, self.bank_shard, k_loc, self.mode, self.lo)
+            keys[:, :k_loc] = self.ops.topk_keys(feature, self.bank_shard, k_loc, self.mode, self.lo, tau0)
         return keys
+
+    def _gather(self, local: torch.Tensor) -> torch.Tensor:
+        """all-gather of (B, c) keys -> (G, B, c), rank-major."""
+        B, c = local.shape
+        gathered = torch.empty((self.world_size * B, c), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(gathered, local.contiguous(), group=self.group)
+        return gathered.view(self.world_size, B, c)
+
+    def global_threshold(self, feature: torch.Tensor, k: int) -> Optional[torch.Tensor]:
+        """Sampling pre-pass across shards: every rank samples its own rows, the per-rank sample
+        lists are all-gathered (B*r keys per rank) and the r-th best of their union — a strided
+        sample of the WHOLE bank — becomes the same admission threshold on every rank.  Shards
+        then only collect rows that can still reach the global top-k, so the per-shard work no
+        longer carries a fixed list warm-up (this is what lets the sharded mode scale)."""
+        if self.mode not in ("bf16", "tf32x3") or self.world_size == 1:
+            return None
+        sk = self.ops.sample_keys(feature, self.bank_shard, k, self.mode, self.n_rows)
+        if sk is None:
+            return None
+        merged = self.ops.merge_keys(self._gather(sk), sk.shape[1])
+        return self.ops.kth_sim(merged)
 
     def topk_keys(self, feature: torch.Tensor, k: int) -> torch.Tensor:
         if k > self.n_rows:
             raise RuntimeError("selected index k out of range")
-        local = self.local_keys(feature, k)
         if self.world_size == 1:
-            return local
-        B = local.shape[0]
-        gathered = torch.empty((self.world_size * B, k), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(gathered, local.contiguous(), group=self.group)  # rank-major concat
-        return self.ops.merge_keys(gathered.view(self.world_size, B, k), k)
+            return self.local_keys(feature, k)
+        tau0 = self.global_threshold(feature, k)
+        merged = self.ops.merge_keys(self._gather(self.local_keys(feature, k, tau0)), k)
+        if tau0 is not None:
+            # identical on every rank, so every rank takes the same branch (collectives stay matched)
+            bad = merged[:, -1] == 0
+            if bool(bad.any()):
+                rows = bad.nonzero(as_tuple=False).view(-1)
+                sub = feature[rows].contiguous()
+                merged[rows] = self.ops.merge_keys(self._gather(self.local_keys(sub, k, None)), k)
+        return merged
 
     def knn_topk(self, feature: torch.Tensor, k: int):
         return self.ops.decode_keys(self.topk_keys(feature, k))

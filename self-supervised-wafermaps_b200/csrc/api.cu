@@ -82,7 +82,8 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
                      const void* bank_hi, const void* bank_lo, int bank_dtype, int bank_layout,
                      int64_t bank_ld, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
                      uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream,
-                     float* dump, int32_t* diag, int flags) {
+                     float* dump, int32_t* diag, int flags, int64_t bank_row_stride = 1,
+                     const float* tau0 = nullptr) {
   if (B < 0 || N <= 0 || dim <= 0) return fail(B200KNN_E_ARG, "topk: bad shape");
   if (k <= 0 || k > N) return fail(B200KNN_E_ARG, "topk: selected index k out of range");
   if (N + idx_offset >= 0xFFFFFFFFll || idx_offset < 0)
@@ -147,6 +148,8 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.split_rows = plan.split_rows;
     p.lists = lists;
     p.out = partial;
+    p.bank_row_stride = bank_row_stride;
+    p.tau0 = tau0;
     const char* why = "";
     e = b200knn::launch_tc(p, plan.grid, plan.cap, st, dump, diag, flags, &why);
     if (e == cudaErrorNotSupported) return fail(B200KNN_E_UNSUPPORTED, "topk(tc): %s", why);
@@ -171,6 +174,18 @@ int b200knn_topk(int mode, const void* q_hi, const void* q_lo, int q_dtype, int6
   return topk_impl(mode, q_hi, q_lo, q_dtype, q_ld, bank_hi, bank_lo, bank_dtype, bank_layout,
                    bank_ld, B, N, dim, k, idx_offset, out_keys, workspace, workspace_bytes, stream,
                    nullptr, nullptr, 0);
+}
+
+int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
+                    const void* bank_lo, int64_t B, int64_t n_visit, int dim, int k, int64_t idx_offset,
+                    int64_t bank_row_stride, const float* tau0, uint64_t* out_keys, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3)
+    return fail(B200KNN_E_ARG, "topk_ex: tensor-core modes only");
+  if (bank_row_stride < 1) return fail(B200KNN_E_ARG, "topk_ex: bank_row_stride must be >= 1");
+  return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, k, idx_offset,
+                   out_keys, workspace, workspace_bytes, stream, nullptr, nullptr, 0, bank_row_stride,
+                   tau0);
 }
 
 // Test hook (not part of the product path): same as b200knn_topk for the tensor-core

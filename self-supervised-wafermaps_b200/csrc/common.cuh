@@ -148,7 +148,7 @@ __device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int
     const int n_valid = __shfl_sync(kFull, int(st.cnt), src);
     const float t = warp_prune<ITEMS>(lists + size_t(src) * CAP, n_valid, k, lane);
     if (lane == src) {
-      st.tau = t;
+      st.tau = fmaxf(st.tau, t);  // never below a caller-supplied initial threshold
       st.cnt = n_valid < k ? n_valid : k;
     }
   }

@@ -70,6 +70,8 @@ struct TcParams {
   int64_t n_qtiles, n_items, split_rows;
   uint64_t* lists;
   uint64_t* out;  // (splits, B, k)
+  int64_t bank_row_stride = 1;  // visit every bank_row_stride-th prepared row (sampling pre-pass)
+  const float* tau0 = nullptr;  // optional (B,) initial admission thresholds
 };
 // returns cudaErrorNotSupported if (D, k) is outside what the kernel handles
 // `dump` (optional, (B,N) fp32) receives the raw similarity tiles (unit tests only);

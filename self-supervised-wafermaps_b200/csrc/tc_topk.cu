@@ -79,6 +79,7 @@ struct TcKernelArgs {
   int64_t n_qtiles, n_items, split_rows;
   uint64_t* lists;
   uint64_t* out;
+  const float* tau0;  // optional (B,) initial admission thresholds (nullptr: -inf)
   float* dump;  // optional (B, N) fp32 similarity dump for unit tests (nullptr in production)
   int32_t* diag;
   int flags;    // experiment switches of the debug entry point (0 in production):
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t grow = m0 + row_in_tile;
       RowState st;
       st.cnt = 0;
-      st.tau = (owner && grow < a.B) ? neg_inf : pos_inf;
+      st.tau = (owner && grow < a.B) ? (a.tau0 != nullptr ? a.tau0[grow] : neg_inf) : pos_inf;
       for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
         const uint32_t buf = tcount & 1u, aphase = (tcount >> 1) & 1u;
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[buf]), aphase, a.diag, 6);
@@ -370,12 +371,12 @@ EncodeTiledFn get_encode() {
 
 // rows x cols matrix of `esize`-byte elements, row pitch = cols*esize; box = box_rows x 128 bytes
 bool make_map(CUtensorMap* m, const void* base, bool bf16, uint64_t rows, uint64_t cols,
-              uint32_t box_rows) {
+              uint32_t box_rows, uint64_t row_stride = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   const uint64_t esize = bf16 ? 2 : 4;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * esize};
+  cuuint64_t gstride[1] = {cols * esize * row_stride};  // row_stride > 1: every row_stride-th row
   cuuint32_t box[2] = {cuuint32_t(kRowBytes / esize), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
@@ -402,6 +403,7 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   a.split_rows = p.split_rows;
   a.lists = p.lists;
   a.out = p.out;
+  a.tau0 = p.tau0;
   a.dump = dump;
   a.diag = diag;
   a.flags = flags;
@@ -420,10 +422,10 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
 
   CUtensorMap mq_hi, mq_lo, mb_hi, mb_lo;
   bool ok = make_map(&mq_hi, p.q_hi, kBf16, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-            make_map(&mb_hi, p.bank_hi, kBf16, uint64_t(p.N), uint64_t(d_pad), BLOCK_N);
+            make_map(&mb_hi, p.bank_hi, kBf16, uint64_t(p.N), uint64_t(d_pad), BLOCK_N, uint64_t(p.bank_row_stride));
   if (ok && !kBf16)
     ok = make_map(&mq_lo, p.q_lo, false, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-         make_map(&mb_lo, p.bank_lo, false, uint64_t(p.N), uint64_t(d_pad), BLOCK_N);
+         make_map(&mb_lo, p.bank_lo, false, uint64_t(p.N), uint64_t(d_pad), BLOCK_N, uint64_t(p.bank_row_stride));
   if (!ok) {
     *why = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;

@@ -16,12 +16,38 @@ from oracle import knn_oracle as O
 
 
 class OracleOps:
-    """numpy/C oracle standing in for the CUDA library on CPU."""
+    """numpy/C oracle standing in for the CUDA library on CPU (same ops contract as _CudaOps)."""
 
-    @staticmethod
-    def topk_keys(feature, bank_shard, k, mode, idx_offset):
-        s, i = O.topk_seqfma(feature.numpy(), bank_shard.numpy(), k, idx_offset)
+    sample_stride = 0      # >0: emulate the sampling pre-pass with this row stride
+    sample_r = 16
+    poison_threshold = False  # force the (1e-7-probability) failure of the sampled bound
+
+    @classmethod
+    def topk_keys(cls, feature, bank_shard, k, mode, idx_offset, tau0=None):
+        sims = O.sims_seqfma(feature.numpy(), bank_shard.numpy())
+        if tau0 is not None:
+            sims = np.where(sims > tau0.numpy()[:, None], sims, -np.inf)
+        s, i = O.canonical_topk_c(sims, k, idx_offset)
+        keys = O.make_keys(s, i)
+        keys[np.isneginf(s)] = 0  # below the threshold: empty slot
+        return torch.from_numpy(keys.view(np.int64))
+
+    @classmethod
+    def sample_keys(cls, feature, bank_shard, k, mode, n_rows_global):
+        if cls.sample_stride == 0:
+            return None
+        sub = bank_shard.numpy()[:, :: cls.sample_stride]
+        r = min(cls.sample_r, sub.shape[1])
+        s, i = O.topk_seqfma(feature.numpy(), np.ascontiguousarray(sub), r)
         return torch.from_numpy(O.make_keys(s, i).view(np.int64))
+
+    @classmethod
+    def kth_sim(cls, keys):
+        s, _ = O.decode_keys(keys.numpy().view(np.uint64))
+        t = torch.from_numpy(np.ascontiguousarray(s[:, -1]))
+        if cls.poison_threshold:
+            t[0] = 10.0  # nothing passes for row 0 -> must be repaired
+        return t
 
     @staticmethod
     def merge_keys(keys_in, k_out):
@@ -44,15 +70,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, out_dir):
+def _worker(rank, world, port, case, out_dir, stride=0, poison=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from b200knn import ShardedBank
 
+        OracleOps.sample_stride, OracleOps.poison_threshold = stride, poison
         c = datagen.make_case(case)
         bank = torch.from_numpy(c["bank"])
-        sb = ShardedBank.from_full(bank, torch.from_numpy(c["labels"]), ops=OracleOps)
+        sb = ShardedBank.from_full(bank, torch.from_numpy(c["labels"]), ops=OracleOps, mode="bf16")
         q = torch.from_numpy(c["feature"])
         keys = sb.topk_keys(q, c["k"])
         pred = sb.knn_predict(q, c["C"], c["k"], c["t"])
@@ -63,9 +90,15 @@ def _worker(rank, world, port, case, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,case", [(2, "clustered_small"), (3, "ragged"), (2, "k5")])
-def test_sharded_equals_single(world, case, tmp_path):
-    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("world,case,stride,poison", [
+    (2, "clustered_small", 0, False),   # no pre-pass
+    (3, "ragged", 0, False),
+    (2, "k5", 0, False),
+    (2, "clustered_small", 4, False),   # global sampled threshold, all-reduced across shards
+    (3, "gauss_small", 4, True),        # ... with one row's threshold forced too high -> repaired
+])
+def test_sharded_equals_single(world, case, stride, poison, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path), stride, poison), nprocs=world, join=True)
     c = datagen.make_case(case)
     s, i = O.topk_seqfma(c["feature"], c["bank"], c["k"])
     want_keys = O.make_keys(s, i).view(np.int64)

@@ -180,3 +180,29 @@ def test_large_bank_against_exact_mode(mode):
         assert torch.equal(tk2, tk[:64])
     else:
         assert recall >= 0.98
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+def test_prepass_threshold_does_not_change_results(mode):
+    """The sampling pre-pass only supplies a starting threshold: keys with it on and off must be
+    bitwise identical (and the repair path must be a no-op or fix every row)."""
+    N, D, k, B = 300000, 512, 200, 200
+    g = torch.Generator(device=DEV).manual_seed(5)
+    bank = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device=DEV), dim=1).t().contiguous()
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device=DEV), dim=1)
+    assert K.prepass_stride(N, k) > 0
+    on = b200knn.topk_keys(q, bank, k, mode=mode)
+    repaired = K.last_prepass_stats["repaired"]
+    K.PREPASS["enabled"] = False
+    try:
+        off = b200knn.topk_keys(q, bank, k, mode=mode)
+    finally:
+        K.PREPASS["enabled"] = True
+    assert torch.equal(on, off)
+    print(f"{mode}: pre-pass repaired rows {repaired}/{B}")
+    # a threshold that is too high for some rows must be repaired, not returned
+    sk = K.sample_keys(q, bank, k, mode)
+    tau = K.kth_sim(sk)
+    tau[:7] = 5.0
+    raw = b200knn.topk_keys(q, bank, k, mode=mode, tau0=tau)
+    assert bool((raw[:7] == 0).all()) and torch.equal(raw[7:], off[7:])
