@@ -120,6 +120,20 @@ int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo,
                     void* stream);
 
 /*
+ * Sampling pre-pass (no counterpart in the reference): the B200KNN_SAMPLE_R = 16 best
+ * SIMILARITIES of every query among prepared bank rows 0, s, 2s, ... (n_visit of them), as
+ * (B,16) keys sorted descending whose index field is 0 (values only — each row's running
+ * top-16 lives in registers, no candidate lists).  The 16-th value seeds b200knn_topk_ex's
+ * tau0.  Workspace: b200knn_topk_workspace_bytes(B, n_visit, dim, 16, mode).
+ */
+#define B200KNN_SAMPLE_R 16
+int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo,
+                        const void* bank_hi, const void* bank_lo, int64_t B,
+                        int64_t n_visit, int dim, int64_t bank_row_stride,
+                        uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/*
  * Merge G sorted candidate lists per query into one (replaces nothing in the
  * reference; it is the exchange step of the bank-row-sharded mode, applied to
  * the buffer an all-gather of per-shard b200knn_topk outputs produces).

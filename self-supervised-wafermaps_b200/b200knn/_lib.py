@@ -18,6 +18,7 @@ _DEFAULT = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb200knn.so"))
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_DN, LAYOUT_ND = 0, 1
 MODE_EXACT, MODE_BF16, MODE_TF32X3, MODE_F32ROWS = 0, 1, 2, 3
+SAMPLE_R = 16  # B200KNN_SAMPLE_R
 MODES = {"exact": MODE_EXACT, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3}
 
 # every symbol include/b200knn.h declares: (restype, argtypes)
@@ -39,6 +40,11 @@ SIGNATURES = {
         c_int,
         [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_int64,
          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "b200knn_topk_sample": (
+        c_int,
+        [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64,
+         c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "b200knn_merge": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "b200knn_decode_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -259,7 +259,9 @@ def _check_feature_bank(feature: torch.Tensor, feature_bank: torch.Tensor) -> No
 # otherwise pays as a fixed cost; rows where the bound fails end with an empty k-th slot and are
 # recomputed without it.
 PREPASS = {"enabled": os.environ.get("B200KNN_PREPASS", "1") == "1", "r": 16, "rank_factor": 5.0,
-           "min_k": 64, "min_sample_rows": 1024}
+           "min_k": 64, "min_sample_rows": 1024,
+           # r == 16: use the values-only kernel variant (row top-16 in registers) for the sample
+           "register_sample": os.environ.get("B200KNN_REGISTER_SAMPLE", "1") == "1"}
 
 
 def prepass_stride(n_rows: int, k: int) -> int:
@@ -270,13 +272,18 @@ def prepass_stride(n_rows: int, k: int) -> int:
     return s if n_rows // s >= PREPASS["min_sample_rows"] else 0
 
 
-def _tc_call(mode, pq, pb, B, n_visit, D, k, idx_offset, stride, tau0, dev, timed=False):
+def _tc_call(mode, pq, pb, B, n_visit, D, k, idx_offset, stride, tau0, dev, timed=False, sample=False):
     lib = _lib.load()
     keys = torch.empty((B, k), dtype=torch.int64, device=dev)
     ws_bytes = lib.b200knn_topk_workspace_bytes(B, n_visit, D, k, _lib.MODES[mode])
     if ws_bytes == 0:
         raise RuntimeError(f"b200knn: unsupported problem (B={B}, N={n_visit}, D={D}, k={k})")
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    if sample:  # values-only sampling variant (k == 16, indices are not produced)
+        _lib.check(lib.b200knn_topk_sample(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(),
+                                           _ptr(pb.lo), B, n_visit, D, stride, keys.data_ptr(), ws.data_ptr(),
+                                           ws_bytes, _stream()), "topk_sample")
+        return keys
     ev = None
     if timed and profile_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -311,7 +318,8 @@ def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode:
     with torch.cuda.device(feature.device):
         pb = bank_cache.get(feature_bank, mode)
         pq = query_cache.get(feature, mode)
-        return _tc_call(mode, pq, pb, B, n_visit, D, r, 0, s, None, feature.device)
+        return _tc_call(mode, pq, pb, B, n_visit, D, r, 0, s, None, feature.device,
+                        sample=(r == _lib.SAMPLE_R and PREPASS["register_sample"]))
 
 
 def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: Optional[str] = None,

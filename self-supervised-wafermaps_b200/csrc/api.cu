@@ -37,7 +37,9 @@ bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan*
   if (mode == B200KNN_MODE_EXACT) {
     *plan = b200knn::make_plan(B, N, k, cap, 128, 128, sms * 2);
   } else {
-    *plan = b200knn::make_plan(B, N, k, cap, 128, b200knn::tc_tile_n(mode, dim), sms);
+    // a worker of the tensor-core kernel is one CTA, or a CTA pair owning 256 query rows
+    const int pair = b200knn::tc_use_pair(mode) ? 2 : 1;
+    *plan = b200knn::make_plan(B, N, k, cap, 128 * pair, b200knn::tc_tile_n(mode, dim), sms / pair);
   }
   return true;
 }
@@ -83,7 +85,7 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
                      int64_t bank_ld, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
                      uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream,
                      float* dump, int32_t* diag, int flags, int64_t bank_row_stride = 1,
-                     const float* tau0 = nullptr) {
+                     const float* tau0 = nullptr, bool sample = false) {
   if (B < 0 || N <= 0 || dim <= 0) return fail(B200KNN_E_ARG, "topk: bad shape");
   if (k <= 0 || k > N) return fail(B200KNN_E_ARG, "topk: selected index k out of range");
   if (N + idx_offset >= 0xFFFFFFFFll || idx_offset < 0)
@@ -150,6 +152,7 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.out = partial;
     p.bank_row_stride = bank_row_stride;
     p.tau0 = tau0;
+    p.sample = sample;
     const char* why = "";
     e = b200knn::launch_tc(p, plan.grid, plan.cap, st, dump, diag, flags, &why);
     if (e == cudaErrorNotSupported) return fail(B200KNN_E_UNSUPPORTED, "topk(tc): %s", why);
@@ -186,6 +189,19 @@ int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo, const void* ba
   return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, k, idx_offset,
                    out_keys, workspace, workspace_bytes, stream, nullptr, nullptr, 0, bank_row_stride,
                    tau0);
+}
+
+int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
+                        const void* bank_lo, int64_t B, int64_t n_visit, int dim,
+                        int64_t bank_row_stride, uint64_t* out_keys, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3)
+    return fail(B200KNN_E_ARG, "topk_sample: tensor-core modes only");
+  if (bank_row_stride < 1) return fail(B200KNN_E_ARG, "topk_sample: bank_row_stride must be >= 1");
+  if (n_visit < B200KNN_SAMPLE_R) return fail(B200KNN_E_ARG, "topk_sample: fewer than 16 rows to sample");
+  return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, B200KNN_SAMPLE_R, 0,
+                   out_keys, workspace, workspace_bytes, stream, nullptr, nullptr, 0, bank_row_stride,
+                   nullptr, true);
 }
 
 // Test hook (not part of the product path): same as b200knn_topk for the tensor-core

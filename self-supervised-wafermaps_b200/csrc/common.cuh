@@ -122,6 +122,67 @@ __device__ __forceinline__ float warp_prune(uint64_t* list, int n_valid, int k, 
                                     : __int_as_float(0xff800000);
 }
 
+// Cheaper prune for the streaming phase: the new threshold only needs the k-th largest
+// SIMILARITY, not a sorted list.  Radix-select over the 32 orderable bits of the sims (one
+// warp-wide count per bit), then compact the keys with sim >= T in place (unsorted; the
+// final flush sorts once).  All keys tied at T are kept, so the kept count can exceed k;
+// returns it in *kept, or -1 if the ties would not leave room to keep appending (the caller
+// then falls back to the exact sort-based prune, which breaks ties by index).
+template <int ITEMS>
+__device__ __forceinline__ float warp_prune_select(uint64_t* list, int n_valid, int k, int lane,
+                                                   int* kept) {
+  constexpr int CAP = ITEMS * 32;
+  uint64_t v[ITEMS];
+  uint32_t hi[ITEMS];
+  uint32_t all_and = 0xffffffffu, all_or = 0u;
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int i = r * 32 + lane;
+    v[r] = (i < n_valid) ? list[i] : 0ull;
+    hi[r] = uint32_t(v[r] >> 32);
+    if (i < n_valid) {
+      all_and &= hi[r];
+      all_or |= hi[r];
+    }
+  }
+  all_and = __reduce_and_sync(kFull, all_and);
+  all_or = __reduce_or_sync(kFull, all_or);
+  // bits on which all sims agree are fixed; search the others from the most significant down
+  uint32_t T = all_and;
+  uint32_t open_bits = all_and ^ all_or;
+  while (open_bits) {
+    const uint32_t bit = 0x80000000u >> __clz(open_bits);
+    open_bits &= ~bit;
+    const uint32_t cand = T | bit;
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) c += (hi[r] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(kFull, c);
+    if (c >= k) T = cand;
+  }
+  // now count(hi >= T) >= k and count(hi > T) < k
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) c += (hi[r] >= T) ? 1 : 0;
+  c = __reduce_add_sync(kFull, c);
+  if (c > k + (CAP - k) / 4) {
+    *kept = -1;
+    return 0.0f;
+  }
+  __syncwarp();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int base = 0;
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const bool keep = hi[r] >= T;  // empty slots have hi == 0 < T
+    const unsigned bm = __ballot_sync(kFull, keep);
+    if (keep) list[base + __popc(bm & lt_mask)] = v[r];
+    base += __popc(bm);
+  }
+  *kept = base;
+  return orderable_to_f32(T);
+}
+
 // Per-row streaming state owned by the row's scanning thread.
 struct RowState {
   float tau;     // admit sims strictly greater than tau (ties lose: bank is scanned in ascending idx)
@@ -134,7 +195,8 @@ struct RowState {
 // slack = free slots every row must keep: the hard bound is the most a row can
 // append before the next call (32 per chunk); callers that run off the critical
 // path pass a larger value to prune early, where it stalls nobody.
-template <int ITEMS>
+// SELECT: prune by radix-select (threshold + unsorted compaction) instead of a full sort.
+template <int ITEMS, bool SELECT = false>
 __device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int k, int lane,
                                               int slack) {
   constexpr int CAP = ITEMS * 32;
@@ -146,10 +208,16 @@ __device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int
     const int src = __ffs(m) - 1;
     m &= m - 1;
     const int n_valid = __shfl_sync(kFull, int(st.cnt), src);
-    const float t = warp_prune<ITEMS>(lists + size_t(src) * CAP, n_valid, k, lane);
+    int kept = -1;
+    float t = 0.0f;
+    if (SELECT) t = warp_prune_select<ITEMS>(lists + size_t(src) * CAP, n_valid, k, lane, &kept);
+    if (kept < 0) {
+      t = warp_prune<ITEMS>(lists + size_t(src) * CAP, n_valid, k, lane);
+      kept = n_valid < k ? n_valid : k;
+    }
     if (lane == src) {
       st.tau = fmaxf(st.tau, t);  // never below a caller-supplied initial threshold
-      st.cnt = n_valid < k ? n_valid : k;
+      st.cnt = uint32_t(kept);
     }
   }
   __syncwarp();

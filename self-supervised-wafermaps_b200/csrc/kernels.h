@@ -72,6 +72,7 @@ struct TcParams {
   uint64_t* out;  // (splits, B, k)
   int64_t bank_row_stride = 1;  // visit every bank_row_stride-th prepared row (sampling pre-pass)
   const float* tau0 = nullptr;  // optional (B,) initial admission thresholds
+  bool sample = false;  // sampling pre-pass: k == 16 best SIMILARITIES per row (keys carry index 0)
 };
 // returns cudaErrorNotSupported if (D, k) is outside what the kernel handles
 // `dump` (optional, (B,N) fp32) receives the raw similarity tiles (unit tests only);
@@ -79,5 +80,6 @@ struct TcParams {
 cudaError_t launch_tc(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
                       int32_t* diag, int flags, const char** why);
 int tc_tile_n(int mode, int dim);
+bool tc_use_pair(int mode);  // BF16 runs as CTA pairs: a worker = 2 CTAs, query tile = 256 rows
 
 }  // namespace b200knn

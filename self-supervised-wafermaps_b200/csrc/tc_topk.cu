@@ -31,6 +31,8 @@
 // so sim(q, n) does not depend on tiling, batch size, split or shard count.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "../../include/b200knn.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -41,6 +43,16 @@ namespace b200knn {
 int tc_tile_n(int mode, int dim) {
   if (mode == B200KNN_MODE_BF16) return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
   return 128;
+}
+
+// BF16 runs as CTA pairs (cta_group::2) unless B200KNN_NO_PAIR=1 (A/B experiments).
+bool tc_use_pair(int mode) {
+  static int no_pair = -1;
+  if (no_pair < 0) {
+    const char* e = getenv("B200KNN_NO_PAIR");
+    no_pair = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return mode == B200KNN_MODE_BF16 && no_pair == 0;
 }
 
 namespace {
@@ -57,6 +69,7 @@ constexpr int kEpiWarps = 4 * kEpiPerQuarter;
 constexpr int kRowsPerWarp = 32 / kEpiPerQuarter;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemLimit = 232448;  // 227 KB
+constexpr int kSampleR = 16;        // values kept per row by the SAMPLE variant (= its k)
 
 struct alignas(16) Barriers {
   uint64_t full[kMaxStages];
@@ -67,7 +80,6 @@ struct alignas(16) Barriers {
   uint64_t q_empty;
   uint32_t tmem_base;
   uint32_t pad;
-  alignas(16) float stage[kEpiWarps][32];  // per epilogue warp: one row's 32-column chunk, lane j <-> column j
 };
 
 struct TcKernelArgs {
@@ -76,7 +88,7 @@ struct TcKernelArgs {
   int n_kblocks;  // D_pad / elements-per-128B-row
   int n_stages;
   int64_t idx_offset;
-  int64_t n_qtiles, n_items, split_rows;
+  int64_t n_qtiles, n_items, split_rows;  // n_qtiles counts 128-row tiles (256-row tile pairs when PAIR)
   uint64_t* lists;
   uint64_t* out;
   const float* tau0;  // optional (B,) initial admission thresholds (nullptr: -inf)
@@ -86,19 +98,36 @@ struct TcKernelArgs {
                 // 1 no selection, 2 no TMEM loads, 4 no MMA issue, 8 no bank TMA loads
 };
 
-template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG>
+// PAIR: two CTAs of a cluster (one TPC) run one tcgen05.mma.cta_group::2 per k-step:
+// M = 256 (each CTA's own resident 128-row query tile), N = BLOCK_N with each CTA
+// loading HALF of the bank tile.  Per SM that halves the bank bytes pulled from L2
+// per MMA cycle and doubles the number of pipeline stages the same smem buys — the
+// 1-CTA kernel was bound by exactly that (3 stages of 32 KB, ~15 TB/s of L2->SM
+// reads chip-wide; profiles/r01_call10_*).  The leader CTA (cluster rank 0) owns the
+// barriers the MMA thread waits on (smem full, query full, TMEM empty); both CTAs'
+// TMA transactions and epilogue arrivals are routed there, and the leader's commits
+// are multicast to both CTAs' smem-empty / TMEM-full / query-empty barriers.
+//
+// SAMPLE: the sampling pre-pass.  Only the kSampleR best SIMILARITIES of every row are
+// wanted (they seed the main pass's admission threshold), so each row's running top-16 lives
+// in its thread's registers (branch-free sorted insert) — no candidate lists, no prunes,
+// no indices.  The general list machinery spent 2/3 of the pre-pass warming up its lists.
+template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG, bool PAIR, bool SAMPLE>
 __global__ void __launch_bounds__(kThreads, 1)
     tc_topk_kernel(const __grid_constant__ CUtensorMap map_q_hi,
                    const __grid_constant__ CUtensorMap map_q_lo,
                    const __grid_constant__ CUtensorMap map_b_hi,
                    const __grid_constant__ CUtensorMap map_b_lo, const TcKernelArgs a) {
   constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);
+  static_assert(!PAIR || kBf16, "CTA pairs are implemented for the BF16 mode");
   constexpr int CAP = ITEMS * 32;
-  constexpr int kBBlockBytes = BLOCK_N * kRowBytes;
+  constexpr int kCtas = PAIR ? 2 : 1;
+  constexpr int kBRows = BLOCK_N / kCtas;  // bank rows of one tile this CTA loads
+  constexpr int kBBlockBytes = kBRows * kRowBytes;
   constexpr int kStageBytes = kBf16 ? kBBlockBytes : 2 * (kABlockBytes + kBBlockBytes);
   constexpr int kElemsPerRow = kBf16 ? 64 : 32;  // elements of one 128-byte k-block row
   constexpr int kUmmaKBytes = 32;                // one MMA consumes 32 bytes of k per row
-  constexpr uint32_t kIdesc = ptx::make_idesc(kBf16 ? 1u : 2u, kTileM, BLOCK_N);
+  constexpr uint32_t kIdesc = ptx::make_idesc(kBf16 ? 1u : 2u, kTileM * kCtas, BLOCK_N);
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -111,6 +140,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  const int64_t worker = PAIR ? int64_t(blockIdx.x >> 1) : int64_t(blockIdx.x);
+  const int64_t n_workers = PAIR ? int64_t(gridDim.x >> 1) : int64_t(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_q_hi);
@@ -125,18 +158,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[b]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[b]), kEpiWarps);  // one arrive per epilogue warp
+      // one arrive per epilogue warp (of both CTAs of a pair: the leader's barrier collects them)
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[b]), kEpiWarps * kCtas);
     }
     ptx::mbar_init(ptx::smem_u32(&bars->q_full), 1);
     ptx::mbar_init(ptx::smem_u32(&bars->q_empty), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), kTmemCols);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(&bars->tmem_base), kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -145,38 +184,49 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, q_phase = 0;
-      for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      for (int64_t item = worker; item < a.n_items; item += n_workers) {
         const int64_t qt = item % a.n_qtiles, sp = item / a.n_qtiles;
-        const int m0 = int(qt * kTileM);
+        const int m0 = int((qt * kCtas + cta_rank) * kTileM);
         const int64_t n_begin = sp * a.split_rows;
         const int64_t n_end = (n_begin + a.split_rows < a.N) ? n_begin + a.split_rows : a.N;
         if (kBf16) {
           ptx::mbar_wait(ptx::smem_u32(&bars->q_empty), q_phase ^ 1, a.diag, 1);
-          ptx::mbar_expect_tx(ptx::smem_u32(&bars->q_full), uint32_t(q_bytes));
-          for (int kb = 0; kb < a.n_kblocks; ++kb)
-            ptx::tma_load_2d(ptx::smem_u32(q_smem + kb * kABlockBytes), &map_q_hi,
-                             kb * kElemsPerRow, m0, ptx::smem_u32(&bars->q_full));
+          if (leader) ptx::mbar_expect_tx(ptx::smem_u32(&bars->q_full), uint32_t(q_bytes) * kCtas);
+          const uint32_t qbar = PAIR ? ptx::mapa(ptx::smem_u32(&bars->q_full), 0) : ptx::smem_u32(&bars->q_full);
+          for (int kb = 0; kb < a.n_kblocks; ++kb) {
+            if (PAIR)
+              ptx::tma_load_2d_pair(ptx::smem_u32(q_smem + kb * kABlockBytes), &map_q_hi,
+                                    kb * kElemsPerRow, m0, qbar);
+            else
+              ptx::tma_load_2d(ptx::smem_u32(q_smem + kb * kABlockBytes), &map_q_hi,
+                               kb * kElemsPerRow, m0, qbar);
+          }
           q_phase ^= 1;
         }
         for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
+          const int nrow = int(n0) + int(cta_rank) * kBRows;  // this CTA's half of the bank tile
           for (int kb = 0; kb < a.n_kblocks; ++kb) {
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, a.diag, 2);
             const uint32_t full = ptx::smem_u32(&bars->full[stage]);
             uint8_t* st = stage_smem + size_t(stage) * kStageBytes;
             if (DEBUG && (a.flags & 8)) {
-              ptx::mbar_arrive(full);
+              if (leader) ptx::mbar_arrive(full);
             } else if (kBf16) {
-              ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
-              ptx::tma_load_2d(ptx::smem_u32(st), &map_b_hi, kb * kElemsPerRow, int(n0), full);
+              if (leader) ptx::mbar_expect_tx(full, uint32_t(kStageBytes) * kCtas);
+              if (PAIR)
+                ptx::tma_load_2d_pair(ptx::smem_u32(st), &map_b_hi, kb * kElemsPerRow, nrow,
+                                      ptx::mapa(full, 0));
+              else
+                ptx::tma_load_2d(ptx::smem_u32(st), &map_b_hi, kb * kElemsPerRow, nrow, full);
             } else {
               ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
               ptx::tma_load_2d(ptx::smem_u32(st), &map_q_hi, kb * kElemsPerRow, m0, full);
               ptx::tma_load_2d(ptx::smem_u32(st + kABlockBytes), &map_q_lo, kb * kElemsPerRow, m0,
                                full);
               ptx::tma_load_2d(ptx::smem_u32(st + 2 * kABlockBytes), &map_b_hi, kb * kElemsPerRow,
-                               int(n0), full);
+                               nrow, full);
               ptx::tma_load_2d(ptx::smem_u32(st + 2 * kABlockBytes + kBBlockBytes), &map_b_lo,
-                               kb * kElemsPerRow, int(n0), full);
+                               kb * kElemsPerRow, nrow, full);
             }
             if (++stage == a.n_stages) {
               stage = 0;
@@ -188,11 +238,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0, q_phase = 0;
       uint32_t tcount = 0;
-      for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      for (int64_t item = worker; item < a.n_items; item += n_workers) {
         const int64_t sp = item / a.n_qtiles;
         const int64_t n_begin = sp * a.split_rows;
         const int64_t n_end = (n_begin + a.split_rows < a.N) ? n_begin + a.split_rows : a.N;
@@ -214,9 +264,12 @@ __global__ void __launch_bounds__(kThreads, 1)
               const uint32_t qa = ptx::smem_u32(q_smem + kb * kABlockBytes);
 #pragma unroll
               for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
-                ptx::umma_f16(tmem_d, ptx::smem_desc_sw128(qa + ks * kUmmaKBytes),
-                              ptx::smem_desc_sw128(st + ks * kUmmaKBytes), kIdesc,
-                              uint32_t((kb | ks) != 0));
+                const uint64_t da = ptx::smem_desc_sw128(qa + ks * kUmmaKBytes);
+                const uint64_t db = ptx::smem_desc_sw128(st + ks * kUmmaKBytes);
+                if (PAIR)
+                  ptx::umma_f16_pair(tmem_d, da, db, kIdesc, uint32_t((kb | ks) != 0));
+                else
+                  ptx::umma_f16(tmem_d, da, db, kIdesc, uint32_t((kb | ks) != 0));
               }
             } else {
               const uint32_t a_hi = st, a_lo = st + kABlockBytes;
@@ -232,16 +285,23 @@ __global__ void __launch_bounds__(kThreads, 1)
                                ptx::smem_desc_sw128(b_hi + o), kIdesc, 1u);
               }
             }
-            ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));  // frees the smem stage
+            // frees the smem stage (in both CTAs of a pair)
+            if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->empty[stage]), 3);
+            else ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
             if (++stage == a.n_stages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          ptx::umma_commit(ptx::smem_u32(&bars->tmem_full[buf]));  // accumulator ready
+          // accumulator ready
+          if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->tmem_full[buf]), 3);
+          else ptx::umma_commit(ptx::smem_u32(&bars->tmem_full[buf]));
           ++tcount;
         }
-        if (kBf16) ptx::umma_commit(ptx::smem_u32(&bars->q_empty));  // query tile reusable
+        if (kBf16) {  // query tile reusable
+          if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->q_empty), 3);
+          else ptx::umma_commit(ptx::smem_u32(&bars->q_empty));
+        }
       }
     }
   } else {
@@ -251,22 +311,29 @@ __global__ void __launch_bounds__(kThreads, 1)
     const bool owner = (lane / kRowsPerWarp) == sub;  // this lane's row is selected by this warp
     const int row_in_tile = quarter * 32 + lane;
     uint64_t* warp_lists = a.lists + (size_t(blockIdx.x) * kTileM + size_t(quarter) * 32) * CAP;
-    const uint32_t stage = ptx::smem_u32(bars->stage[warp - 2]);
+    uint64_t* my_list = warp_lists + size_t(lane) * CAP;
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
-    const unsigned lt_mask = (1u << lane) - 1u;
+    // the barrier the MMA thread waits on before overwriting an accumulator buffer
+    const uint32_t tmem_empty_bar0 = PAIR ? ptx::mapa(ptx::smem_u32(&bars->tmem_empty[0]), 0)
+                                          : ptx::smem_u32(&bars->tmem_empty[0]);
+    const uint32_t tmem_empty_bar1 = PAIR ? ptx::mapa(ptx::smem_u32(&bars->tmem_empty[1]), 0)
+                                          : ptx::smem_u32(&bars->tmem_empty[1]);
     // free slots below which a row is pruned between tiles (off the critical path)
     const int soft_slack = min(96, (CAP - a.k) / 2);
     uint32_t tcount = 0;
-    for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    for (int64_t item = worker; item < a.n_items; item += n_workers) {
       const int64_t qt = item % a.n_qtiles, sp = item / a.n_qtiles;
-      const int64_t m0 = qt * kTileM;
+      const int64_t m0 = (qt * kCtas + cta_rank) * kTileM;
       const int64_t n_begin = sp * a.split_rows;
       const int64_t n_end = (n_begin + a.split_rows < a.N) ? n_begin + a.split_rows : a.N;
       const int64_t grow = m0 + row_in_tile;
       RowState st;
       st.cnt = 0;
       st.tau = (owner && grow < a.B) ? (a.tau0 != nullptr ? a.tau0[grow] : neg_inf) : pos_inf;
+      float top[SAMPLE ? kSampleR : 1];  // SAMPLE: this row's best similarities, descending
+#pragma unroll
+      for (int i = 0; i < (SAMPLE ? kSampleR : 1); ++i) top[i] = neg_inf;
       for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
         const uint32_t buf = tcount & 1u, aphase = (tcount >> 1) & 1u;
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[buf]), aphase, a.diag, 6);
@@ -285,7 +352,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             // all of this warp's TMEM reads of the buffer are done: hand it back
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[buf]));
+            if (lane == 0) {
+              const uint32_t bar = buf ? tmem_empty_bar1 : tmem_empty_bar0;
+              if (PAIR) ptx::mbar_arrive_cluster(bar);
+              else ptx::mbar_arrive(bar);
+            }
           }
           if (DEBUG && a.dump != nullptr && owner && grow < a.B) {
 #pragma unroll
@@ -294,41 +365,86 @@ __global__ void __launch_bounds__(kThreads, 1)
               if (gn < n_end) a.dump[grow * a.N + gn] = s[j];
             }
           }
+          if (n0 + c0 + 32 > n_end) {
+            // ragged end of the split: columns past it (zero-filled by TMA) never qualify
+            const int nv = int(n_end - (n0 + c0));
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= nv) s[j] = neg_inf;
+          }
           float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
           for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
           const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          unsigned hits = __ballot_sync(kFull, mx > st.tau);
-          if (DEBUG && (a.flags & 1)) hits = 0;
-          if (hits == 0) continue;
-          // ---- some row of this warp has a candidate in this chunk (about half the chunks)
-          const int64_t gn = n0 + c0 + lane;
-          const bool col_ok = gn < n_end;
-          const uint32_t gidx = uint32_t(gn + a.idx_offset);
-          while (hits) {
-            const int r = __ffs(hits) - 1;
-            hits &= hits - 1;
-            if (lane == r) {
+          const bool hit = mx > st.tau;
+          if (!__any_sync(kFull, hit) || (DEBUG && (a.flags & 1))) continue;
+          // ---- some rows of this warp have candidates in this chunk.  Every such row's
+          // thread appends its own candidates straight from its registers; rows proceed in
+          // parallel, so the cost does not grow with the number of rows that hit.
+          if (hit) {
+            // bit j of m: column j qualifies.  Only the column classes (j mod 4) whose partial
+            // maximum qualifies are tested; no per-column branches.
+            unsigned m = 0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                ptx::st_shared_v4(stage + j * 4, s[j], s[j + 1], s[j + 2], s[j + 3]);
+            for (int c = 0; c < 4; ++c) {
+              if (m4[c] > st.tau) {
+#pragma unroll
+                for (int j = c; j < 32; j += 4) m |= (s[j] > st.tau) ? (1u << j) : 0u;
+              }
             }
-            __syncwarp();
-            const float v = ptx::ld_shared_f32(stage + lane * 4);
-            const float tr = __shfl_sync(kFull, st.tau, r);
-            const uint32_t cr = __shfl_sync(kFull, st.cnt, r);
-            const bool p = (v > tr) && col_ok;
-            const unsigned pm = __ballot_sync(kFull, p);
-            if (p) warp_lists[size_t(r) * CAP + cr + __popc(pm & lt_mask)] = make_key(v, gidx);
-            if (lane == r) st.cnt += __popc(pm);
-            __syncwarp();
+            const bool single = (m & (m - 1u)) == 0u;  // the common case: the row maximum alone
+            if (SAMPLE) {
+              auto insert = [&](float x) {
+#pragma unroll
+                for (int i = 0; i < kSampleR; ++i) {
+                  const float hi = fmaxf(top[i], x);
+                  x = fminf(top[i], x);
+                  top[i] = hi;
+                }
+              };
+              if (single) {
+                insert(mx);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if ((m >> j) & 1u) insert(s[j]);
+              }
+              st.tau = top[kSampleR - 1];  // only rows that can hit get here (others hold +inf)
+            } else {
+              const uint32_t gidx0 = uint32_t(n0 + c0 + a.idx_offset);
+              if (single) {
+                my_list[st.cnt] = make_key(mx, gidx0 + uint32_t(__ffs(m) - 1));
+                st.cnt += 1;
+              } else {
+                uint64_t* lp = my_list + st.cnt;
+                uint32_t c = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if ((m >> j) & 1u) {
+                    lp[c] = make_key(s[j], gidx0 + uint32_t(j));
+                    ++c;
+                  }
+                }
+                st.cnt += c;
+              }
+            }
           }
-          warp_maintain<ITEMS>(warp_lists, st, a.k, lane, 32);  // emergency only (list would overflow)
+          if (SAMPLE) continue;
+          __syncwarp();
+          warp_maintain<ITEMS, true>(warp_lists, st, a.k, lane, 32);  // emergency only (list would overflow)
         }
         // The TMEM buffer went back to the MMA warp before the last chunk was processed:
         // prune here, off the accumulator's critical path, a little before it becomes mandatory.
-        warp_maintain<ITEMS>(warp_lists, st, a.k, lane, soft_slack);
+        if (!SAMPLE) warp_maintain<ITEMS, true>(warp_lists, st, a.k, lane, soft_slack);
         ++tcount;
+      }
+      if (SAMPLE) {
+        if (owner && grow < a.B) {
+          uint64_t* o = a.out + (size_t(sp) * a.B + grow) * kSampleR;
+#pragma unroll
+          for (int i = 0; i < kSampleR; ++i) o[i] = top[i] > neg_inf ? make_key(top[i], 0u) : 0ull;
+        }
+        continue;
       }
       const int64_t row0 = m0 + quarter * 32;
       unsigned valid = 0;
@@ -343,10 +459,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -386,10 +503,12 @@ bool make_map(CUtensorMap* m, const void* base, bool bf16, uint64_t rows, uint64
   return r == CUDA_SUCCESS;
 }
 
-template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG>
+template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG, bool PAIR, bool SAMPLE = false>
 cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* dump, int32_t* diag,
                      int flags, const char** why) {
   constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);
+  constexpr int kCtas = PAIR ? 2 : 1;
+  constexpr int kBRows = BLOCK_N / kCtas;
   const int d_pad = (p.D + 63) / 64 * 64;
   const int elems_per_row = kBf16 ? 64 : 32;
   TcKernelArgs a;
@@ -407,7 +526,7 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   a.dump = dump;
   a.diag = diag;
   a.flags = flags;
-  const int b_block = BLOCK_N * kRowBytes;
+  const int b_block = kBRows * kRowBytes;
   const int stage_bytes = kBf16 ? b_block : 2 * (kABlockBytes + b_block);
   const int q_bytes = kBf16 ? a.n_kblocks * kABlockBytes : 0;
   const int fixed = q_bytes + int(sizeof(Barriers)) + 1024;  // 1024: manual alignment slack
@@ -422,10 +541,10 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
 
   CUtensorMap mq_hi, mq_lo, mb_hi, mb_lo;
   bool ok = make_map(&mq_hi, p.q_hi, kBf16, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-            make_map(&mb_hi, p.bank_hi, kBf16, uint64_t(p.N), uint64_t(d_pad), BLOCK_N, uint64_t(p.bank_row_stride));
+            make_map(&mb_hi, p.bank_hi, kBf16, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
   if (ok && !kBf16)
     ok = make_map(&mq_lo, p.q_lo, false, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-         make_map(&mb_lo, p.bank_lo, false, uint64_t(p.N), uint64_t(d_pad), BLOCK_N, uint64_t(p.bank_row_stride));
+         make_map(&mb_lo, p.bank_lo, false, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
   if (!ok) {
     *why = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
@@ -434,22 +553,41 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
     mq_lo = mq_hi;
     mb_lo = mb_hi;
   }
-  auto kern = tc_topk_kernel<MODE, BLOCK_N, ITEMS, DEBUG>;
+  auto kern = tc_topk_kernel<MODE, BLOCK_N, ITEMS, DEBUG, PAIR, SAMPLE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, smem, stream>>>(mq_hi, mq_lo, mb_hi, mb_lo, a);
-  return cudaGetLastError();
+  // `grid` counts workers: CTAs, or CTA pairs (clusters of 2 on one TPC) when PAIR
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(grid * kCtas));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, mq_hi, mq_lo, mb_hi, mb_lo, a);
 }
 
-template <int MODE, int BLOCK_N, bool DEBUG>
+template <int MODE, int BLOCK_N, bool DEBUG, bool PAIR>
 cudaError_t launch_cap(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
                        int32_t* diag, int flags, const char** why) {
+  if (p.sample) {
+    if (DEBUG || p.k != kSampleR || p.tau0 != nullptr) {
+      *why = "the sampling variant keeps exactly 16 values per row";
+      return cudaErrorNotSupported;
+    }
+    return launch_t<MODE, BLOCK_N, 2, false, PAIR, true>(p, grid, stream, nullptr, diag, 0, why);
+  }
   switch (cap) {
-    case 64: return launch_t<MODE, BLOCK_N, 2, DEBUG>(p, grid, stream, dump, diag, flags, why);
-    case 128: return launch_t<MODE, BLOCK_N, 4, DEBUG>(p, grid, stream, dump, diag, flags, why);
-    case 256: return launch_t<MODE, BLOCK_N, 8, DEBUG>(p, grid, stream, dump, diag, flags, why);
-    case 512: return launch_t<MODE, BLOCK_N, 16, DEBUG>(p, grid, stream, dump, diag, flags, why);
-    case 1024: return launch_t<MODE, BLOCK_N, 32, DEBUG>(p, grid, stream, dump, diag, flags, why);
+    case 64: return launch_t<MODE, BLOCK_N, 2, DEBUG, PAIR>(p, grid, stream, dump, diag, flags, why);
+    case 128: return launch_t<MODE, BLOCK_N, 4, DEBUG, PAIR>(p, grid, stream, dump, diag, flags, why);
+    case 256: return launch_t<MODE, BLOCK_N, 8, DEBUG, PAIR>(p, grid, stream, dump, diag, flags, why);
+    case 512: return launch_t<MODE, BLOCK_N, 16, DEBUG, PAIR>(p, grid, stream, dump, diag, flags, why);
+    case 1024: return launch_t<MODE, BLOCK_N, 32, DEBUG, PAIR>(p, grid, stream, dump, diag, flags, why);
     default: *why = "unsupported k"; return cudaErrorNotSupported;
   }
 }
@@ -458,12 +596,16 @@ template <bool DEBUG>
 cudaError_t launch_mode(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
                         int32_t* diag, int flags, const char** why) {
   if (p.mode == B200KNN_MODE_BF16) {
-    if (tc_tile_n(p.mode, p.D) == 256)
-      return launch_cap<B200KNN_MODE_BF16, 256, DEBUG>(p, grid, cap, stream, dump, diag, flags, why);
-    return launch_cap<B200KNN_MODE_BF16, 128, DEBUG>(p, grid, cap, stream, dump, diag, flags, why);
+    const bool wide = tc_tile_n(p.mode, p.D) == 256;
+    if (tc_use_pair(p.mode)) {
+      if (wide) return launch_cap<B200KNN_MODE_BF16, 256, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
+      return launch_cap<B200KNN_MODE_BF16, 128, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
+    }
+    if (wide) return launch_cap<B200KNN_MODE_BF16, 256, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
+    return launch_cap<B200KNN_MODE_BF16, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
   }
   if (p.mode == B200KNN_MODE_TF32X3)
-    return launch_cap<B200KNN_MODE_TF32X3, 128, DEBUG>(p, grid, cap, stream, dump, diag, flags, why);
+    return launch_cap<B200KNN_MODE_TF32X3, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
   *why = "unknown mode";
   return cudaErrorNotSupported;
 }

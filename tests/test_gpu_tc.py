@@ -206,3 +206,24 @@ def test_prepass_threshold_does_not_change_results(mode):
     tau[:7] = 5.0
     raw = b200knn.topk_keys(q, bank, k, mode=mode, tau0=tau)
     assert bool((raw[:7] == 0).all()) and torch.equal(raw[7:], off[7:])
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("B,N,stride", [(200, 300000, 62), (513, 40000, 8), (64, 811457, 62), (3, 4096, 1)])
+def test_register_sample_equals_list_sample(mode, B, N, stride):
+    """b200knn_topk_sample (row top-16 kept in registers, values only) must return bit for bit the
+    similarities of the general list-based top-16 over the same strided rows."""
+    D = 512
+    g = torch.Generator(device=DEV).manual_seed(11)
+    bank = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device=DEV), dim=1).t().contiguous()
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device=DEV), dim=1)
+    pb = K.bank_cache.get(bank, mode)
+    pq = K.prepare_rows(q, mode, vectors_are_columns=False)
+    n_visit = (N + stride - 1) // stride
+    lists = K._tc_call(mode, pq, pb, B, n_visit, D, 16, 0, stride, None, q.device)
+    regs = K._tc_call(mode, pq, pb, B, n_visit, D, 16, 0, stride, None, q.device, sample=True)
+    s_list, _ = b200knn.decode_keys(lists)
+    s_reg, i_reg = b200knn.decode_keys(regs)
+    assert torch.equal(s_list.view(torch.int32), s_reg.view(torch.int32))
+    assert bool((i_reg == 0).all())
+    assert torch.equal(K.kth_sim(lists), K.kth_sim(regs))
