@@ -181,7 +181,7 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 }
 // arrive on an mbarrier anywhere in the cluster (address from mapa)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar)
                : "memory");
 }
 // 2-D tiled load issued by either CTA of a pair: data lands in THIS CTA's smem, the

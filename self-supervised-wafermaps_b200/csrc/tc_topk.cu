@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* stage_smem = smem + q_bytes;
   Barriers* bars = reinterpret_cast<Barriers*>(stage_smem + size_t(a.n_stages) * kStageBytes);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle so the compiler knows it is warp-uniform (role code then
+  // lives in uniform registers instead of being re-broadcast around every TMA/MMA instruction)
+  const int warp = __shfl_sync(kFull, int(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
   const bool leader = (cta_rank == 0);
@@ -181,9 +183,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the (uniform) loop and waits; one elected lane issues.
+    {
       int stage = 0;
       uint32_t phase = 0, q_phase = 0;
+      const uint32_t qbar = PAIR ? ptx::mapa(ptx::smem_u32(&bars->q_full), 0) : ptx::smem_u32(&bars->q_full);
       for (int64_t item = worker; item < a.n_items; item += n_workers) {
         const int64_t qt = item % a.n_qtiles, sp = item / a.n_qtiles;
         const int m0 = int((qt * kCtas + cta_rank) * kTileM);
@@ -191,43 +195,45 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int64_t n_end = (n_begin + a.split_rows < a.N) ? n_begin + a.split_rows : a.N;
         if (kBf16) {
           ptx::mbar_wait(ptx::smem_u32(&bars->q_empty), q_phase ^ 1, a.diag, 1);
-          if (leader) ptx::mbar_expect_tx(ptx::smem_u32(&bars->q_full), uint32_t(q_bytes) * kCtas);
-          const uint32_t qbar = PAIR ? ptx::mapa(ptx::smem_u32(&bars->q_full), 0) : ptx::smem_u32(&bars->q_full);
-          for (int kb = 0; kb < a.n_kblocks; ++kb) {
-            if (PAIR)
-              ptx::tma_load_2d_pair(ptx::smem_u32(q_smem + kb * kABlockBytes), &map_q_hi,
-                                    kb * kElemsPerRow, m0, qbar);
-            else
-              ptx::tma_load_2d(ptx::smem_u32(q_smem + kb * kABlockBytes), &map_q_hi,
-                               kb * kElemsPerRow, m0, qbar);
+          if (ptx::elect_one()) {
+            if (leader) ptx::mbar_expect_tx(ptx::smem_u32(&bars->q_full), uint32_t(q_bytes) * kCtas);
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+              if (PAIR)
+                ptx::tma_load_2d_pair(ptx::smem_u32(q_smem + kb * kABlockBytes), &map_q_hi,
+                                      kb * kElemsPerRow, m0, qbar);
+              else
+                ptx::tma_load_2d(ptx::smem_u32(q_smem + kb * kABlockBytes), &map_q_hi,
+                                 kb * kElemsPerRow, m0, qbar);
+            }
           }
+          __syncwarp();
           q_phase ^= 1;
         }
         for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
           const int nrow = int(n0) + int(cta_rank) * kBRows;  // this CTA's half of the bank tile
           for (int kb = 0; kb < a.n_kblocks; ++kb) {
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, a.diag, 2);
-            const uint32_t full = ptx::smem_u32(&bars->full[stage]);
-            uint8_t* st = stage_smem + size_t(stage) * kStageBytes;
-            if (DEBUG && (a.flags & 8)) {
-              if (leader) ptx::mbar_arrive(full);
-            } else if (kBf16) {
-              if (leader) ptx::mbar_expect_tx(full, uint32_t(kStageBytes) * kCtas);
-              if (PAIR)
-                ptx::tma_load_2d_pair(ptx::smem_u32(st), &map_b_hi, kb * kElemsPerRow, nrow,
-                                      ptx::mapa(full, 0));
-              else
-                ptx::tma_load_2d(ptx::smem_u32(st), &map_b_hi, kb * kElemsPerRow, nrow, full);
-            } else {
-              ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
-              ptx::tma_load_2d(ptx::smem_u32(st), &map_q_hi, kb * kElemsPerRow, m0, full);
-              ptx::tma_load_2d(ptx::smem_u32(st + kABlockBytes), &map_q_lo, kb * kElemsPerRow, m0,
-                               full);
-              ptx::tma_load_2d(ptx::smem_u32(st + 2 * kABlockBytes), &map_b_hi, kb * kElemsPerRow,
-                               nrow, full);
-              ptx::tma_load_2d(ptx::smem_u32(st + 2 * kABlockBytes + kBBlockBytes), &map_b_lo,
-                               kb * kElemsPerRow, nrow, full);
+            if (ptx::elect_one()) {
+              const uint32_t full = ptx::smem_u32(&bars->full[stage]);
+              const uint32_t st = ptx::smem_u32(stage_smem + size_t(stage) * kStageBytes);
+              if (DEBUG && (a.flags & 8)) {
+                if (leader) ptx::mbar_arrive(full);
+              } else if (kBf16) {
+                if (leader) ptx::mbar_expect_tx(full, uint32_t(kStageBytes) * kCtas);
+                if (PAIR)
+                  ptx::tma_load_2d_pair(st, &map_b_hi, kb * kElemsPerRow, nrow, ptx::mapa(full, 0));
+                else
+                  ptx::tma_load_2d(st, &map_b_hi, kb * kElemsPerRow, nrow, full);
+              } else {
+                ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
+                ptx::tma_load_2d(st, &map_q_hi, kb * kElemsPerRow, m0, full);
+                ptx::tma_load_2d(st + kABlockBytes, &map_q_lo, kb * kElemsPerRow, m0, full);
+                ptx::tma_load_2d(st + 2 * kABlockBytes, &map_b_hi, kb * kElemsPerRow, nrow, full);
+                ptx::tma_load_2d(st + 2 * kABlockBytes + kBBlockBytes, &map_b_lo, kb * kElemsPerRow,
+                                 nrow, full);
+              }
             }
+            __syncwarp();
             if (++stage == a.n_stages) {
               stage = 0;
               phase ^= 1;
@@ -238,10 +244,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0 && leader) {
+    // Warp-uniform loop (all lanes wait on the barriers); one elected lane issues the MMAs
+    // and commits.  Descriptors differ only in their 14-bit address field.
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0, q_phase = 0;
       uint32_t tcount = 0;
+      const uint64_t desc0 = ptx::smem_desc_sw128(0);
+      const uint32_t q_base = ptx::smem_u32(q_smem), st_base = ptx::smem_u32(stage_smem);
       for (int64_t item = worker; item < a.n_items; item += n_workers) {
         const int64_t sp = item / a.n_qtiles;
         const int64_t n_begin = sp * a.split_rows;
@@ -258,49 +268,55 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int kb = 0; kb < a.n_kblocks; ++kb) {
             ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase, a.diag, 5);
             ptx::tc_fence_after();
-            const uint32_t st = ptx::smem_u32(stage_smem + size_t(stage) * kStageBytes);
-            if (DEBUG && (a.flags & 4)) {
-            } else if (kBf16) {
-              const uint32_t qa = ptx::smem_u32(q_smem + kb * kABlockBytes);
+            if (ptx::elect_one()) {
+              const uint32_t st = st_base + uint32_t(stage) * uint32_t(kStageBytes);
+              if (DEBUG && (a.flags & 4)) {
+              } else if (kBf16) {
+                const uint64_t da = desc0 + uint64_t(((q_base + uint32_t(kb) * kABlockBytes) & 0x3FFFFu) >> 4);
+                const uint64_t db = desc0 + uint64_t((st & 0x3FFFFu) >> 4);
 #pragma unroll
-              for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
-                const uint64_t da = ptx::smem_desc_sw128(qa + ks * kUmmaKBytes);
-                const uint64_t db = ptx::smem_desc_sw128(st + ks * kUmmaKBytes);
-                if (PAIR)
-                  ptx::umma_f16_pair(tmem_d, da, db, kIdesc, uint32_t((kb | ks) != 0));
-                else
-                  ptx::umma_f16(tmem_d, da, db, kIdesc, uint32_t((kb | ks) != 0));
+                for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
+                  const uint64_t o = uint64_t((ks * kUmmaKBytes) >> 4);
+                  if (PAIR)
+                    ptx::umma_f16_pair(tmem_d, da + o, db + o, kIdesc, uint32_t((kb | ks) != 0));
+                  else
+                    ptx::umma_f16(tmem_d, da + o, db + o, kIdesc, uint32_t((kb | ks) != 0));
+                }
+              } else {
+                const uint64_t a_hi = desc0 + uint64_t((st & 0x3FFFFu) >> 4);
+                const uint64_t a_lo = a_hi + uint64_t(kABlockBytes >> 4);
+                const uint64_t b_hi = a_hi + uint64_t((2 * kABlockBytes) >> 4);
+                const uint64_t b_lo = b_hi + uint64_t(kBBlockBytes >> 4);
+#pragma unroll
+                for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
+                  const uint64_t o = uint64_t((ks * kUmmaKBytes) >> 4);
+                  ptx::umma_tf32(tmem_d, a_hi + o, b_lo + o, kIdesc, uint32_t((kb | ks) != 0));
+                  ptx::umma_tf32(tmem_d, a_lo + o, b_hi + o, kIdesc, 1u);
+                  ptx::umma_tf32(tmem_d, a_hi + o, b_hi + o, kIdesc, 1u);
+                }
               }
-            } else {
-              const uint32_t a_hi = st, a_lo = st + kABlockBytes;
-              const uint32_t b_hi = st + 2 * kABlockBytes, b_lo = b_hi + kBBlockBytes;
-#pragma unroll
-              for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
-                const uint32_t o = ks * kUmmaKBytes;
-                ptx::umma_tf32(tmem_d, ptx::smem_desc_sw128(a_hi + o),
-                               ptx::smem_desc_sw128(b_lo + o), kIdesc, uint32_t((kb | ks) != 0));
-                ptx::umma_tf32(tmem_d, ptx::smem_desc_sw128(a_lo + o),
-                               ptx::smem_desc_sw128(b_hi + o), kIdesc, 1u);
-                ptx::umma_tf32(tmem_d, ptx::smem_desc_sw128(a_hi + o),
-                               ptx::smem_desc_sw128(b_hi + o), kIdesc, 1u);
+              // frees the smem stage (in both CTAs of a pair)
+              if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->empty[stage]), 3);
+              else ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
+              if (kb + 1 == a.n_kblocks) {  // accumulator ready
+                if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->tmem_full[buf]), 3);
+                else ptx::umma_commit(ptx::smem_u32(&bars->tmem_full[buf]));
               }
             }
-            // frees the smem stage (in both CTAs of a pair)
-            if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->empty[stage]), 3);
-            else ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
+            __syncwarp();
             if (++stage == a.n_stages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          // accumulator ready
-          if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->tmem_full[buf]), 3);
-          else ptx::umma_commit(ptx::smem_u32(&bars->tmem_full[buf]));
           ++tcount;
         }
         if (kBf16) {  // query tile reusable
-          if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->q_empty), 3);
-          else ptx::umma_commit(ptx::smem_u32(&bars->q_empty));
+          if (ptx::elect_one()) {
+            if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->q_empty), 3);
+            else ptx::umma_commit(ptx::smem_u32(&bars->q_empty));
+          }
+          __syncwarp();
         }
       }
     }
