@@ -177,7 +177,9 @@ int b200knn_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
  *              E = err_coef * ||q_b|| * (*bank_max_norm)  — the candidate set is
  *              then not proven to contain the true top-k and the caller must
  *              recompute row b in MODE_EXACT; *n_uncertified counts such rows
- *              (caller zeroes it).
+ *              (caller zeroes it).  A row whose k_in-th candidate slot is empty
+ *              although k_in < N (a b200knn_topk_ex threshold starved it) is
+ *              uncertified as well.
  * b200knn_row_norm_max writes max_n ||row_n|| (x1.001) to *out_dev.
  */
 int b200knn_row_norm_max(const float* rows_a, const float* rows_b, int64_t n,

@@ -69,6 +69,37 @@ SIGNATURES = {
 
 _lib = None
 
+# kernels each C entry point launches (bench.py's gpu_launches; a b200knn_topk* call whose plan
+# splits the bank launches one more, the split merge — bench.py adds those from plan_info)
+KERNELS_PER_CALL = {
+    "b200knn_prepare_rows": 1, "b200knn_topk": 1, "b200knn_topk_ex": 1, "b200knn_topk_sample": 1,
+    "b200knn_merge": 1, "b200knn_decode_keys": 1, "b200knn_vote": 1, "b200knn_rescore": 1,
+    "b200knn_row_norm_max": 1, "b200knn_debug_topk_dump": 1,
+}
+launch_counter = {"kernels": 0}
+
+
+class _CountingLib:
+    """Thin proxy over the CDLL that counts kernel launches made through the C ABI."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+            n = KERNELS_PER_CALL.get(name, 0)
+            if n:
+                def fn(*args, _raw=raw, _n=n):
+                    launch_counter["kernels"] += _n
+                    return _raw(*args)
+            else:
+                fn = raw
+            self._cache[name] = fn
+        return fn
+
 
 def lib_path() -> str:
     return os.environ.get("B200KNN_LIB", _DEFAULT)
@@ -91,8 +122,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    _lib = lib
-    return lib
+    _lib = _CountingLib(lib)
+    return _lib
 
 
 def check(rc: int, what: str) -> None:

@@ -323,12 +323,14 @@ def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode:
 
 
 def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: Optional[str] = None,
-              idx_offset: int = 0, tau0: Optional[torch.Tensor] = None) -> torch.Tensor:
+              idx_offset: int = 0, tau0: Optional[torch.Tensor] = None, repair: bool = True) -> torch.Tensor:
     """(B,k) selection keys (uint64 bit patterns in an int64 tensor), sorted descending under
     the canonical (sim desc, bank index asc) order; bank indices are offset by idx_offset.
 
     tau0 (tensor-core modes): caller-supplied (B,) admission thresholds — then no pre-pass and
-    no validation happen here and rows may come back with empty (0) slots (sharded driver)."""
+    no validation happen here and rows may come back with empty (0) slots (sharded driver).
+    repair=False (tensor-core modes): skip the host-synchronising check for rows the sampled
+    threshold starved (empty k-th slot); the caller detects and repairs them (``repair_rows``)."""
     lib = _lib.load()
     mode = mode or _default_mode
     if mode in RESCORED_MODES:
@@ -377,8 +379,23 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
         if sk is None:
             return _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, None, dev, timed=True)
         keys = _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, kth_sim(sk), dev, timed=True)
+        if not repair:
+            return keys
         return _repair_rows(keys, lambda rows: _tc_call(mode, _rows_of(pq, rows), pb, rows.numel(), N, D, k,
                                                         idx_offset, 1, None, dev))
+
+
+def recompute_rows(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str, rows: torch.Tensor,
+                   idx_offset: int = 0) -> torch.Tensor:
+    """Keys of the given query rows computed without any admission threshold."""
+    sub = feature[rows].contiguous()
+    if mode == "exact" or mode in RESCORED_MODES:
+        return topk_keys(sub, feature_bank, k, "exact", idx_offset)
+    B, D = sub.shape
+    with torch.cuda.device(feature.device):
+        pb = bank_cache.get(feature_bank, mode)
+        pq = prepare_rows(sub, mode, vectors_are_columns=False)
+        return _tc_call(mode, pq, pb, B, feature_bank.shape[1], D, k, idx_offset, 1, None, feature.device)
 
 
 def _rows_of(pq: "PreparedRows", rows: torch.Tensor) -> "PreparedRows":
@@ -403,7 +420,7 @@ last_prepass_stats = {"rows": 0, "repaired": 0}
 
 
 def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
-                        idx_offset: int = 0) -> torch.Tensor:
+                        idx_offset: int = 0, defer: bool = False):
     """Tensor-core candidates (k_in = k + margin) -> exact sequential-fma re-scoring -> best k,
     with a per-row certificate; uncertified rows are recomputed in "exact" mode, so the keys are
     bitwise those of mode "exact"."""
@@ -420,7 +437,9 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
     out = torch.empty((B, k), dtype=torch.int64, device=dev)
     if B == 0:
         return out
-    cand = topk_keys(feature, feature_bank, k_in, cfg["cand"], idx_offset)
+    # no repair pass on the candidates: a row its sampled threshold starved has an empty k_in-th
+    # slot, which the re-scoring kernel reports as uncertified (-> exact recomputation below)
+    cand = topk_keys(feature, feature_bank, k_in, cfg["cand"], idx_offset, repair=False)
     pb = bank_cache.get(feature_bank, cfg["cand"])
     rows_a, rows_b = pb.rescore_rows()
     max_norm = pb.max_norm()
@@ -434,6 +453,8 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
                                        _ptr(rows_b), N, D, cand.data_ptr(), B, k_in, k, idx_offset,
                                        float(cfg["err_coef"]), max_norm.data_ptr(), out.data_ptr(),
                                        flags.data_ptr(), n_bad.data_ptr(), _stream()), "rescore")
+        if defer:  # the caller reads n_bad in its own (single) synchronisation and fixes the rows
+            return out, flags, n_bad
         bad = int(n_bad.item())
         last_rescore_stats["rows"] = B
         last_rescore_stats["uncertified"] = bad
@@ -469,7 +490,8 @@ def merge_keys(keys_in: torch.Tensor, k_out: int) -> torch.Tensor:
 
 
 def vote(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn_t: float,
-         label_offset: int = 0, return_scores: bool = False, check_labels: bool = True):
+         label_offset: int = 0, return_scores: bool = False, check_labels: bool = True,
+         return_flag: bool = False):
     """keys (B,k) + labels (N,) -> (B,C) int64 class ranking (score desc, class asc)."""
     lib = _lib.load()
     _require_cuda("feature_labels", feature_labels)
@@ -496,6 +518,8 @@ def vote(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn
                                        f"[0, num_classes={C})")
                 if f == 2:
                     raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
+    if return_flag:  # device int32[1]: 0 ok, 1 label outside [0,C), 2 neighbour index outside labels
+        return pred, (flag if B else torch.zeros((1,), dtype=torch.int32, device=dev))
     return (pred, scores) if return_scores else pred
 
 
@@ -513,11 +537,46 @@ def knn_predict(feature: torch.Tensor, feature_bank: torch.Tensor, feature_label
     (score desc, class id asc).
     """
     _require_cuda("feature_labels", feature_labels)
-    keys = topk_keys(feature, feature_bank, knn_k)
+    mode = _default_mode
     if feature_labels.numel() != feature_bank.shape[1]:
+        _check_feature_bank(feature, feature_bank)
         raise RuntimeError(
             f"feature_labels has {feature_labels.numel()} entries for a bank of {feature_bank.shape[1]}")
-    return vote(keys, feature_labels, num_classes, knn_t)
+    if mode == "exact":
+        return vote(topk_keys(feature, feature_bank, knn_k, mode), feature_labels, num_classes, knn_t)
+    # Tensor-core modes: everything is enqueued first and ONE host synchronisation reads the
+    # status word: bit 0/1 vote flag (label / index out of range), bit 2 rows to recompute (rows a
+    # sampled threshold starved, or rows whose exact re-scoring could not be certified).
+    dev = feature.device
+    if mode in RESCORED_MODES:
+        keys, bad_rows, n_bad = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True)
+        if n_bad is None:  # B == 0
+            return vote(keys, feature_labels, num_classes, knn_t)
+    else:
+        keys = topk_keys(feature, feature_bank, knn_k, mode, repair=False)
+        if keys.shape[0] == 0:
+            return vote(keys, feature_labels, num_classes, knn_t)
+        bad_rows = keys[:, -1] == 0
+        n_bad = bad_rows.sum().to(torch.int32).view(1)
+    pred, flag = vote(keys, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
+    status = torch.stack([flag.view(()), n_bad.view(()).to(torch.int32)]).tolist()
+    n_fix = int(status[1])
+    if mode in RESCORED_MODES:
+        last_rescore_stats["rows"], last_rescore_stats["uncertified"] = keys.shape[0], n_fix
+    else:
+        last_prepass_stats["rows"], last_prepass_stats["repaired"] = keys.shape[0], n_fix
+    if n_fix:
+        rows = bad_rows.nonzero(as_tuple=False).view(-1)
+        fixed = recompute_rows(feature, feature_bank, knn_k, mode, rows)
+        pred[rows], flag2 = vote(fixed, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
+        status[0] = max(int(status[0]), int(flag2.item()))
+    if status[0] == 1:
+        # the reference raises here from zeros(...).scatter(...) (lightly knn_predict)
+        raise RuntimeError("index out of bounds: a feature_labels entry is outside "
+                           f"[0, num_classes={int(num_classes)})")
+    if status[0] == 2:
+        raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
+    return pred
 
 
 def knn_topk(feature: torch.Tensor, feature_bank: torch.Tensor, k: int,

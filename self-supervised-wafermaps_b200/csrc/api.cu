@@ -268,6 +268,7 @@ int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_
   p.B = B;
   p.k_in = k_in;
   p.k_out = k_out;
+  p.all_rows = (int64_t(k_in) >= N) ? 1 : 0;
   p.idx_offset = idx_offset;
   p.err_coef = err_coef;
   p.bank_max_norm = bank_max_norm;

@@ -46,6 +46,7 @@ struct RescoreParams {
   const uint64_t* cand;  // (B, k_in) candidate keys, sorted descending under the approximate sims
   int64_t B;
   int k_in, k_out;
+  int all_rows;  // k_in >= N: every bank row is a candidate, empty slots are legitimate
   int64_t idx_offset;
   float err_coef;
   const float* bank_max_norm;  // device scalar

@@ -109,7 +109,11 @@ __global__ void __launch_bounds__(kWarps * 32)
     if (lane == 0) {
       const uint64_t last = cand[p.k_in - 1];  // worst candidate under the approximate order
       int ok = 1;
-      if (last != 0) {  // an empty slot means every bank row was a candidate
+      if (last == 0) {
+        // an empty slot certifies the row only when every bank row was a candidate (k_in >= N);
+        // otherwise the candidate pass ran under an admission threshold that starved this row
+        ok = p.all_rows ? 1 : 0;
+      } else {
         const float qn = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.001f;
         const float e = p.err_coef * qn * (*p.bank_max_norm);
         ok = (kth != 0) && (key_sim(kth) > key_sim(last) + e);

@@ -58,6 +58,10 @@ class OracleOps:
         s, i = O.decode_keys(keys.numpy().view(np.uint64))
         return torch.from_numpy(O.vote_o64(s, i, labels.numpy(), num_classes, knn_t)[0])
 
+    @classmethod
+    def vote_flag(cls, keys, labels, num_classes, knn_t):
+        return cls.vote(keys, labels, num_classes, knn_t), torch.zeros(1, dtype=torch.int32)
+
     @staticmethod
     def decode_keys(keys):
         s, i = O.decode_keys(keys.numpy().view(np.uint64))
@@ -82,7 +86,9 @@ def _worker(rank, world, port, case, out_dir, stride=0, poison=False):
         sb = ShardedBank.from_full(bank, torch.from_numpy(c["labels"]), ops=OracleOps, mode="bf16")
         q = torch.from_numpy(c["feature"])
         keys = sb.topk_keys(q, c["k"])
-        pred = sb.knn_predict(q, c["C"], c["k"], c["t"])
+        pred = sb.knn_predict(q, c["C"], c["k"], c["t"])  # all-to-all by query slice (default)
+        pred_ag = sb.knn_predict(q, c["C"], c["k"], c["t"], exchange="allgather")
+        assert torch.equal(pred, pred_ag)
         np.save(os.path.join(out_dir, f"keys_{rank}.npy"), keys.numpy())
         np.save(os.path.join(out_dir, f"pred_{rank}.npy"), pred.numpy())
         dist.barrier()
