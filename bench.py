@@ -309,6 +309,14 @@ def main():
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
 
+    phases = None
+    if world > 1:  # where a sharded step spends its time (one extra untimed step, rank 0's view)
+        sb.phase_log = []
+        step_resident()
+        torch.cuda.synchronize()
+        log, sb.phase_log = sb.phase_log, None
+        phases = {log[i][0]: round(log[i - 1][1].elapsed_time(log[i][1]), 3) for i in range(1, len(log))}
+
     if rank == 0:
         pk = peaks()
         ms_per_step = total_ms / args.steps
@@ -362,6 +370,9 @@ def main():
             "gpu_launches": gpu_launches,
             "clocks": clocks.summary(),
         }
+        if phases is not None:
+            line["config"]["phases_ms"] = phases
+            line["config"]["exchange"] = "all-to-all of (B,k) keys by query slice + all-gather of (B,C) rankings (NCCL)"
         if mode in K.RESCORED_MODES:
             line["config"]["uncertified_rows_last_step"] = K.last_rescore_stats["uncertified"]
         line["config"]["prepass"] = {"stride": K.prepass_stride(N, k_plan), "r": K.PREPASS["r"],

@@ -26,7 +26,9 @@ for (N, D, B, k, C) in [(200000, 512, 300, 200, 9), (30000, 512, 130, 20, 38), (
         sharded = sb.topk_keys(q, k)
         b200knn.set_default_mode(mode)
         p1 = b200knn.knn_predict(q, bank, lab, C, k, 0.1)
-        p2 = sb.knn_predict(q, C, k, 0.1)
+        p2 = sb.knn_predict(q, C, k, 0.1)                        # all-to-all by query slice (default)
+        p3 = sb.knn_predict(q, C, k, 0.1, exchange="allgather")  # the literal all-gather of keys
+        assert torch.equal(p2, p3), "exchange variants disagree"
         # bf16: per-shard similarities are bitwise those of the unsharded run as well (fixed-order
         # accumulation, no split-K), so even the approximate mode is shard-count invariant
         same = bool(torch.equal(single, sharded)) and bool(torch.equal(p1, p2))

@@ -272,9 +272,12 @@ def prepass_stride(n_rows: int, k: int) -> int:
     return s if n_rows // s >= PREPASS["min_sample_rows"] else 0
 
 
-def _tc_call(mode, pq, pb, B, n_visit, D, k, idx_offset, stride, tau0, dev, timed=False, sample=False):
+def _tc_call(mode, pq, pb, B, n_visit, D, k, idx_offset, stride, tau0, dev, timed=False, sample=False,
+             out=None):
     lib = _lib.load()
-    keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+    if out is not None:
+        assert out.shape == (B, k) and out.dtype == torch.int64 and out.is_contiguous()
+    keys = out if out is not None else torch.empty((B, k), dtype=torch.int64, device=dev)
     ws_bytes = lib.b200knn_topk_workspace_bytes(B, n_visit, D, k, _lib.MODES[mode])
     if ws_bytes == 0:
         raise RuntimeError(f"b200knn: unsupported problem (B={B}, N={n_visit}, D={D}, k={k})")
@@ -323,7 +326,8 @@ def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode:
 
 
 def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: Optional[str] = None,
-              idx_offset: int = 0, tau0: Optional[torch.Tensor] = None, repair: bool = True) -> torch.Tensor:
+              idx_offset: int = 0, tau0: Optional[torch.Tensor] = None, repair: bool = True,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(B,k) selection keys (uint64 bit patterns in an int64 tensor), sorted descending under
     the canonical (sim desc, bank index asc) order; bank indices are offset by idx_offset.
 
@@ -373,8 +377,8 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
             return keys
         pb = bank_cache.get(feature_bank, mode)
         pq = query_cache.get(feature, mode)
-        if tau0 is not None:
-            return _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, tau0.contiguous(), dev, timed=True)
+        if tau0 is not None:  # `out`: write the keys straight into a caller buffer (sharded exchange)
+            return _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, tau0.contiguous(), dev, timed=True, out=out)
         sk = sample_keys(feature, feature_bank, k, mode)
         if sk is None:
             return _tc_call(mode, pq, pb, B, N, D, k, idx_offset, 1, None, dev, timed=True)

@@ -45,6 +45,15 @@ class _CudaOps:
         return topk_keys(feature, bank_shard, k, mode, idx_offset, tau0)
 
     @staticmethod
+    def topk_into(feature, bank_shard, k, mode, idx_offset, tau0, out):
+        """topk_keys writing into `out` when the mode allows it (tensor-core mode with a threshold)."""
+        from .knn import topk_keys
+        if tau0 is not None and mode in ("bf16", "tf32x3"):
+            topk_keys(feature, bank_shard, k, mode, idx_offset, tau0, out=out)
+        else:
+            out.copy_(topk_keys(feature, bank_shard, k, mode, idx_offset, tau0))
+
+    @staticmethod
     def sample_keys(feature, bank_shard, k, mode, n_rows_global):
         from .knn import sample_keys
         return sample_keys(feature, bank_shard, k, mode, n_rows_global)
@@ -159,6 +168,15 @@ class ShardedBank:
     def knn_topk(self, feature: torch.Tensor, k: int):
         return self.ops.decode_keys(self.topk_keys(feature, k))
 
+    # measurement hook (bench.py --phases): CUDA events between the phases of knn_predict
+    phase_log = None
+
+    def _mark(self, name: str) -> None:
+        if self.phase_log is not None and torch.cuda.is_available():
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_log.append((name, ev))
+
     # ------------------------------------------------------------------ all-to-all exchange
     def _owned(self, B: int) -> Tuple[int, int, int]:
         """(rows per rank, first owned query row, one past the last owned row) for B queries."""
@@ -180,9 +198,15 @@ class ShardedBank:
         per, _, _ = self._owned(B)
         rows = self.hi - self.lo
         k_loc = min(k, rows)
-        local = torch.zeros((per * self.world_size, k), dtype=torch.int64, device=feature.device)
-        if k_loc > 0 and B > 0:
-            local[:B, :k_loc] = self.ops.topk_keys(feature, self.bank_shard, k_loc, self.mode, self.lo, tau0)
+        if k_loc == k and B > 0 and hasattr(self.ops, "topk_into"):
+            # the kernel writes its keys straight into the exchange buffer; only the pad rows are zeroed
+            local = torch.empty((per * self.world_size, k), dtype=torch.int64, device=feature.device)
+            local[B:].zero_()
+            self.ops.topk_into(feature, self.bank_shard, k, self.mode, self.lo, tau0, local[:B])
+        else:
+            local = torch.zeros((per * self.world_size, k), dtype=torch.int64, device=feature.device)
+            if k_loc > 0 and B > 0:
+                local[:B, :k_loc] = self.ops.topk_keys(feature, self.bank_shard, k_loc, self.mode, self.lo, tau0)
         return self.ops.merge_keys(self._exchange_owned(local, per), k)
 
     def knn_predict(self, feature: torch.Tensor, num_classes: int, knn_k: int = 200,
@@ -196,8 +220,12 @@ class ShardedBank:
             raise RuntimeError("selected index k out of range")
         B, C = feature.shape[0], int(num_classes)
         per, lo, hi = self._owned(B)
+        mark = self._mark
+        mark("start")
         tau0 = self.global_threshold(feature, knn_k)
+        mark("threshold")  # sample + all-gather of (B,16) + merge
         merged = self.owned_keys(feature, knn_k, tau0)
+        mark("topk+exchange+merge")
         pred, flag = self.ops.vote_flag(merged, self.labels, C, knn_t)
         # (per, C+1): class ranking + a status column (bit 0: starved row, bits 1..: vote flag << 1)
         packed = torch.zeros((per, C + 1), dtype=torch.int64, device=feature.device)
@@ -208,6 +236,7 @@ class ShardedBank:
         packed[0, C] += flag.to(torch.int64).view(()) * 2
         gathered = torch.empty((per * self.world_size, C + 1), dtype=torch.int64, device=feature.device)
         dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        mark("vote+gather")
         status = gathered[:B, C]
         out = gathered[:B, :C].contiguous()
         worst = int(status.max().item()) if B else 0  # the one host synchronisation of the call

@@ -223,9 +223,30 @@ __device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int
   __syncwarp();
 }
 
+// Sort the first n (<= S*32) keys of `list` descending and write the best k to `o`
+// (zero-padded).
+template <int S>
+__device__ __forceinline__ void sort_store(const uint64_t* list, int n, int k, int lane, uint64_t* o) {
+  uint64_t v[S];
+#pragma unroll
+  for (int r = 0; r < S; ++r) {
+    const int i = r * 32 + lane;
+    v[r] = (i < n) ? list[i] : 0ull;
+  }
+  warp_sort_desc<S>(v, lane);
+#pragma unroll
+  for (int r = 0; r < S; ++r) {
+    const int i = r * 32 + lane;
+    if (i < k) o[i] = v[r];
+  }
+  for (int i = S * 32 + lane; i < k; i += 32) o[i] = 0ull;  // k beyond this network: empty slots
+}
+
 // End of a work item: every row of the warp is pruned one last time and its
 // best k keys (sorted descending, zero-padded) are written to `out` (row r of
-// the warp at out + r*out_stride) if row_valid.
+// the warp at out + r*out_stride) if row_valid.  The sorting network is sized to
+// the row's candidate count (rows that ran under a good threshold hold few), and
+// long lists are first cut to ~k by radix-select.
 template <int ITEMS>
 __device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, int k, int lane,
                                            uint64_t* out, size_t out_stride, unsigned valid_mask) {
@@ -233,21 +254,20 @@ __device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, 
   __syncwarp();
   for (int src = 0; src < 32; ++src) {
     if (!((valid_mask >> src) & 1u)) continue;
-    const int n_valid = __shfl_sync(kFull, int(st.cnt), src);
+    int n_valid = __shfl_sync(kFull, int(st.cnt), src);
     uint64_t* list = lists + size_t(src) * CAP;
-    uint64_t v[ITEMS];
-#pragma unroll
-    for (int r = 0; r < ITEMS; ++r) {
-      const int i = r * 32 + lane;
-      v[r] = (i < n_valid) ? list[i] : 0ull;
-    }
-    warp_sort_desc<ITEMS>(v, lane);
     uint64_t* o = out + size_t(src) * out_stride;
-#pragma unroll
-    for (int r = 0; r < ITEMS; ++r) {
-      const int i = r * 32 + lane;
-      if (i < k) o[i] = v[r];
+    if (ITEMS > 8 && n_valid > 256 && n_valid > k) {
+      int kept = -1;
+      warp_prune_select<ITEMS>(list, n_valid, k, lane, &kept);
+      if (kept >= 0) n_valid = kept;
+      __syncwarp();
     }
+    if (n_valid <= 64) sort_store<2>(list, n_valid, k, lane, o);
+    else if (ITEMS >= 4 && n_valid <= 128) sort_store<(ITEMS >= 4 ? 4 : ITEMS)>(list, n_valid, k, lane, o);
+    else if (ITEMS >= 8 && n_valid <= 256) sort_store<(ITEMS >= 8 ? 8 : ITEMS)>(list, n_valid, k, lane, o);
+    else if (ITEMS >= 16 && n_valid <= 512) sort_store<(ITEMS >= 16 ? 16 : ITEMS)>(list, n_valid, k, lane, o);
+    else sort_store<ITEMS>(list, n_valid, k, lane, o);
   }
   __syncwarp();
 }

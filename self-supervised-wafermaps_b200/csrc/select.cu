@@ -11,39 +11,86 @@
 namespace b200knn {
 namespace {
 
-// one warp per query row; HBM-bound: reads G*k_in*8 B, writes k_out*8 B per row
+// One warp per query row.  The warp streams the G lists into a CAP-slot buffer in shared
+// memory, SKIPPING empty slots (lists are sorted descending, so the first empty key ends a
+// list): shards and bank splits that ran under a shared admission threshold return mostly
+// empty lists, and the union of their non-empty keys usually fits the buffer, i.e. one sort
+// per row instead of one per list.  When the buffer fills it is pruned (sort, keep k_out).
+// HBM-bound: reads <= G*k_in*8 B, writes k_out*8 B per row.
 template <int ITEMS>
 __global__ void __launch_bounds__(128) merge_kernel(const uint64_t* __restrict__ in, int G,
                                                     int64_t B, int k_in, int k_out,
                                                     uint64_t* __restrict__ out) {
   constexpr int CAP = ITEMS * 32;
+  extern __shared__ __align__(16) uint64_t merge_smem[];
   const int lane = threadIdx.x & 31;
-  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= B) return;
-  const int64_t total = int64_t(G) * k_in;
-  auto fetch = [&](int64_t t) -> uint64_t {
-    if (t >= total) return 0ull;
-    const int64_t g = t / k_in, j = t - g * k_in;
-    return in[(g * B + row) * k_in + j];
-  };
-  uint64_t v[ITEMS];
-#pragma unroll
-  for (int r = 0; r < ITEMS; ++r) v[r] = fetch(r * 32 + lane);
-  warp_sort_desc<ITEMS>(v, lane);
-  int64_t next = CAP;
-  while (next < total) {
+  uint64_t* buf = merge_smem + size_t(warp) * CAP;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int cnt = 0;
+
+  auto prune = [&]() {  // sort the buffer, keep the best k_out
+    uint64_t v[ITEMS];
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
       const int i = r * 32 + lane;
-      if (i >= k_out) v[r] = fetch(next + (i - k_out));
+      v[r] = i < cnt ? buf[i] : 0ull;
     }
-    next += CAP - k_out;
     warp_sort_desc<ITEMS>(v, lane);
-  }
 #pragma unroll
-  for (int r = 0; r < ITEMS; ++r) {
-    const int i = r * 32 + lane;
-    if (i < k_out) out[row * k_out + i] = v[r];
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = r * 32 + lane;
+      if (i < k_out) buf[i] = v[r];
+    }
+    cnt = cnt < k_out ? cnt : k_out;
+    __syncwarp();
+  };
+  // returns true when the chunk held an empty key (the rest of that list is empty too)
+  auto push = [&](uint64_t key) -> bool {
+    const bool nz = key != 0ull;
+    const unsigned bm = __ballot_sync(kFull, nz);
+    if (bm == 0u) return true;
+    if (cnt + 32 > CAP) prune();
+    if (nz) buf[cnt + __popc(bm & lt_mask)] = key;
+    cnt += __popc(bm);
+    return bm != kFull;
+  };
+
+  constexpr int kAhead = 4;  // first chunks of several lists are fetched together (latency)
+  for (int g0 = 0; g0 < G; g0 += kAhead) {
+    uint64_t first[kAhead];
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      const int g = g0 + u;
+      first[u] = (g < G && lane < k_in) ? in[(int64_t(g) * B + row) * k_in + lane] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      const int g = g0 + u;
+      if (g >= G) break;
+      bool done = push(first[u]);
+      const uint64_t* list = in + (int64_t(g) * B + row) * k_in;
+      for (int j0 = 32; j0 < k_in && !done; j0 += 32)
+        done = push(j0 + lane < k_in ? list[j0 + lane] : 0ull);
+    }
+  }
+  {
+    uint64_t v[ITEMS];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = r * 32 + lane;
+      v[r] = i < cnt ? buf[i] : 0ull;
+    }
+    warp_sort_desc<ITEMS>(v, lane);
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = r * 32 + lane;
+      if (i < k_out) out[row * k_out + i] = v[r];
+    }
   }
 }
 
@@ -59,9 +106,11 @@ __global__ void decode_kernel(const uint64_t* __restrict__ keys, int64_t n, floa
 template <int ITEMS>
 cudaError_t launch_merge_t(const uint64_t* in, int G, int64_t B, int k_in, int k_out, uint64_t* out,
                            cudaStream_t stream) {
-  const int warps = 4;
+  // few rows: one warp per CTA so that the rows spread over the SMs
+  const int warps = B >= 148 * 8 ? 4 : 1;
   const int64_t blocks = (B + warps - 1) / warps;
-  merge_kernel<ITEMS><<<unsigned(blocks), warps * 32, 0, stream>>>(in, G, B, k_in, k_out, out);
+  const size_t smem = size_t(warps) * ITEMS * 32 * sizeof(uint64_t);
+  merge_kernel<ITEMS><<<unsigned(blocks), warps * 32, smem, stream>>>(in, G, B, k_in, k_out, out);
   return cudaGetLastError();
 }
 
