@@ -120,11 +120,12 @@ int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo,
                     void* stream);
 
 /*
- * Sampling pre-pass (no counterpart in the reference): the B200KNN_SAMPLE_R = 16 best
- * SIMILARITIES of every query among prepared bank rows 0, s, 2s, ... (n_visit of them), as
- * (B,16) keys sorted descending whose index field is 0 (values only — each row's running
- * top-16 lives in registers, no candidate lists).  The 16-th value seeds b200knn_topk_ex's
- * tau0.  Workspace: b200knn_topk_workspace_bytes(B, n_visit, dim, 16, mode).
+ * Sampling pre-pass (no counterpart in the reference): for every query, the
+ * B200KNN_SAMPLE_R = 16 best 32-column CHUNK MAXIMA of its similarities with prepared bank
+ * rows 0, s, 2s, ... (n_visit of them), as (B,16) keys sorted descending whose index field
+ * is 0 (values only — each row's running top-16 lives in registers, no candidate lists).
+ * Every returned value is a sampled similarity and the 16-th is <= the 16-th best sampled
+ * similarity, so it is a valid seed for b200knn_topk_ex's tau0.  Workspace: b200knn_topk_workspace_bytes(B, n_visit, dim, 16, mode).
  */
 #define B200KNN_SAMPLE_R 16
 int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo,
@@ -162,6 +163,23 @@ int b200knn_decode_keys(const uint64_t* keys, int64_t n_keys, float* sims,
 int b200knn_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
                  int64_t n_labels, int64_t label_offset, int C, double t,
                  int64_t* pred, double* scores, int32_t* err_flag, void* stream);
+
+/*
+ * b200knn_vote writing into a wider row-major buffer: pred has row stride pred_ld >= C, and
+ * when status_col >= C a per-row status word is stored in that column: bit 0 = the row's
+ * k-th key slot is empty (a b200knn_topk_ex threshold starved it), bit 1 = a label outside
+ * [0,C), bit 2 = a neighbour index outside the labels.  The sharded driver all-gathers this
+ * (B_owned, C+1) buffer as it is.
+ */
+int b200knn_vote_ex(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
+                    int64_t n_labels, int64_t label_offset, int C, double t,
+                    int64_t* pred, int64_t pred_ld, int status_col, double* scores,
+                    int32_t* err_flag, void* stream);
+
+/* out[b] = similarity of keys[b, j] (-inf for an empty slot): the threshold a (B,r) sample
+ * hands to b200knn_topk_ex (j = r-1). */
+int b200knn_key_sim_column(const uint64_t* keys, int64_t B, int k, int j, float* out,
+                           void* stream);
 
 /*
  * Exact re-scoring of tensor-core candidates (the "fp32" mode; no counterpart in

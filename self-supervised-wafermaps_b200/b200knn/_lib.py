@@ -53,6 +53,12 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p,
          c_void_p, c_void_p],
     ),
+    "b200knn_vote_ex": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int, c_double, c_void_p, c_int64, c_int,
+         c_void_p, c_void_p, c_void_p],
+    ),
+    "b200knn_key_sim_column": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "b200knn_row_norm_max": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "b200knn_rescore": (
         c_int,
@@ -73,7 +79,8 @@ _lib = None
 # splits the bank launches one more, the split merge — bench.py adds those from plan_info)
 KERNELS_PER_CALL = {
     "b200knn_prepare_rows": 1, "b200knn_topk": 1, "b200knn_topk_ex": 1, "b200knn_topk_sample": 1,
-    "b200knn_merge": 1, "b200knn_decode_keys": 1, "b200knn_vote": 1, "b200knn_rescore": 1,
+    "b200knn_merge": 1, "b200knn_decode_keys": 1, "b200knn_vote": 1, "b200knn_vote_ex": 1,
+    "b200knn_key_sim_column": 1, "b200knn_rescore": 1,
     "b200knn_row_norm_max": 1, "b200knn_debug_topk_dump": 1,
 }
 launch_counter = {"kernels": 0}

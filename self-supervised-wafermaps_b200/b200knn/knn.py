@@ -303,7 +303,35 @@ def _tc_call(mode, pq, pb, B, n_visit, D, k, idx_offset, stride, tau0, dev, time
 
 def kth_sim(keys: torch.Tensor) -> torch.Tensor:
     """Similarity of the last key of every row (-inf for an empty slot): a (B,) fp32 tensor."""
-    return decode_keys(keys[:, -1:].contiguous())[0].view(-1).contiguous()
+    B, k = keys.shape
+    out = torch.empty((B,), dtype=torch.float32, device=keys.device)
+    if B:
+        keys = keys.contiguous()
+        with torch.cuda.device(keys.device):
+            _lib.check(_lib.load().b200knn_key_sim_column(keys.data_ptr(), B, k, k - 1, out.data_ptr(),
+                                                          _stream()), "key_sim_column")
+    return out
+
+
+def vote_packed(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn_t: float,
+                n_rows_out: int) -> torch.Tensor:
+    """(n_rows_out, C+1) int64: class rankings of keys' rows in columns [0,C) and the per-row
+    status word of b200knn_vote_ex in column C; rows past keys.shape[0] are zero."""
+    lib = _lib.load()
+    B, k = keys.shape
+    C = int(num_classes)
+    labels = feature_labels if feature_labels.dtype == torch.int64 else feature_labels.long()
+    labels = labels.contiguous().view(-1)
+    dev = keys.device
+    out = torch.zeros((n_rows_out, C + 1), dtype=torch.int64, device=dev) if n_rows_out > B \
+        else torch.empty((n_rows_out, C + 1), dtype=torch.int64, device=dev)
+    if B:
+        with torch.cuda.device(dev):
+            flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+            _lib.check(lib.b200knn_vote_ex(keys.data_ptr(), labels.data_ptr(), B, k, labels.numel(), 0, C,
+                                           float(knn_t), out.data_ptr(), C + 1, C, None, flag.data_ptr(),
+                                           _stream()), "vote_ex")
+    return out
 
 
 def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,

@@ -74,11 +74,11 @@ class _CudaOps:
         return vote(keys, labels, num_classes, knn_t)
 
     @staticmethod
-    def vote_flag(keys, labels, num_classes, knn_t):
-        """vote without the host-side check: (pred, device int32[1] flag) — the caller folds the
-        flag into its own single synchronisation."""
-        from .knn import vote
-        return vote(keys, labels, num_classes, knn_t, check_labels=False, return_flag=True)
+    def vote_packed(keys, labels, num_classes, knn_t, n_rows_out):
+        """(n_rows_out, C+1): class rankings + per-row status word (bit 0 starved row, bit 1 label
+        out of range, bit 2 index out of range); no host synchronisation."""
+        from .knn import vote_packed
+        return vote_packed(keys, labels, num_classes, knn_t, n_rows_out)
 
     @staticmethod
     def decode_keys(keys):
@@ -146,7 +146,10 @@ class ShardedBank:
         sk = self.ops.sample_keys(feature, self.bank_shard, k, self.mode, self.n_rows)
         if sk is None:
             return None
-        merged = self.ops.merge_keys(self._gather(sk), sk.shape[1])
+        self._mark("  sample")
+        g = self._gather(sk)
+        self._mark("  gather(B,16)")
+        merged = self.ops.merge_keys(g, sk.shape[1])
         return self.ops.kth_sim(merged)
 
     def topk_keys(self, feature: torch.Tensor, k: int) -> torch.Tensor:
@@ -203,16 +206,19 @@ class ShardedBank:
             local = torch.empty((per * self.world_size, k), dtype=torch.int64, device=feature.device)
             local[B:].zero_()
             self.ops.topk_into(feature, self.bank_shard, k, self.mode, self.lo, tau0, local[:B])
+            self._mark("  local topk")
         else:
             local = torch.zeros((per * self.world_size, k), dtype=torch.int64, device=feature.device)
             if k_loc > 0 and B > 0:
                 local[:B, :k_loc] = self.ops.topk_keys(feature, self.bank_shard, k_loc, self.mode, self.lo, tau0)
-        return self.ops.merge_keys(self._exchange_owned(local, per), k)
+        recv = self._exchange_owned(local, per)
+        self._mark("  all-to-all")
+        return self.ops.merge_keys(recv, k)
 
     def knn_predict(self, feature: torch.Tensor, num_classes: int, knn_k: int = 200,
                     knn_t: float = 0.1, exchange: str = "alltoall") -> torch.Tensor:
         """Same contract as ``knn_predict`` with the bank sharded; identical on every rank."""
-        if exchange == "allgather" or self.world_size == 1 or not hasattr(self.ops, "vote_flag"):
+        if exchange == "allgather" or self.world_size == 1 or not hasattr(self.ops, "vote_packed"):
             return self.ops.vote(self.topk_keys(feature, knn_k), self.labels, num_classes, knn_t)
         if exchange != "alltoall":
             raise ValueError(f"unknown exchange {exchange!r}")
@@ -226,25 +232,18 @@ class ShardedBank:
         mark("threshold")  # sample + all-gather of (B,16) + merge
         merged = self.owned_keys(feature, knn_k, tau0)
         mark("topk+exchange+merge")
-        pred, flag = self.ops.vote_flag(merged, self.labels, C, knn_t)
-        # (per, C+1): class ranking + a status column (bit 0: starved row, bits 1..: vote flag << 1)
-        packed = torch.zeros((per, C + 1), dtype=torch.int64, device=feature.device)
-        packed[:, :C] = pred
-        n_own = hi - lo
-        if n_own > 0:
-            packed[:n_own, C] = (merged[:n_own, -1] == 0).to(torch.int64)
-        packed[0, C] += flag.to(torch.int64).view(()) * 2
+        # (per, C+1): class ranking + a status column, for the owned rows only (pad rows stay 0)
+        packed = self.ops.vote_packed(merged[:hi - lo], self.labels, C, knn_t, per)
         gathered = torch.empty((per * self.world_size, C + 1), dtype=torch.int64, device=feature.device)
         dist.all_gather_into_tensor(gathered, packed, group=self.group)
         mark("vote+gather")
         status = gathered[:B, C]
         out = gathered[:B, :C].contiguous()
         worst = int(status.max().item()) if B else 0  # the one host synchronisation of the call
-        if worst >= 2:
-            f = worst >> 1
-            if f & 1:
-                raise RuntimeError("index out of bounds: a feature_labels entry is outside "
-                                   f"[0, num_classes={C})")
+        if worst & 2:
+            raise RuntimeError("index out of bounds: a feature_labels entry is outside "
+                               f"[0, num_classes={C})")
+        if worst & 4:
             raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
         if worst == 1:
             # identical on every rank -> every rank takes this branch: recompute the starved rows

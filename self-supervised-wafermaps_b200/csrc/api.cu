@@ -285,16 +285,31 @@ int b200knn_decode_keys(const uint64_t* keys, int64_t n_keys, float* sims, int64
   return e == cudaSuccess ? B200KNN_OK : fail_cuda("decode_keys", e);
 }
 
+int b200knn_vote_ex(const uint64_t* keys, const int64_t* labels, int64_t B, int k, int64_t n_labels,
+                    int64_t label_offset, int C, double t, int64_t* pred, int64_t pred_ld,
+                    int status_col, double* scores, int32_t* err_flag, void* stream) {
+  if (!keys || !labels || !pred || !err_flag || B < 0 || k <= 0 || C <= 0 || n_labels <= 0)
+    return fail(B200KNN_E_ARG, "vote: bad argument");
+  if (pred_ld < C || status_col >= pred_ld || (status_col >= 0 && status_col < C))
+    return fail(B200KNN_E_ARG, "vote: pred_ld / status_col do not describe a (B, >=C) output");
+  if (!(t > 0.0) && !(t < 0.0)) return fail(B200KNN_E_ARG, "vote: temperature must be non-zero");
+  cudaError_t e = b200knn::launch_vote(keys, labels, B, k, n_labels, label_offset, C, t, pred, pred_ld,
+                                       status_col, scores, err_flag, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidValue) return fail(B200KNN_E_UNSUPPORTED, "vote: k/num_classes too large for shared memory");
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("vote", e);
+}
+
 int b200knn_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k, int64_t n_labels,
                  int64_t label_offset, int C, double t, int64_t* pred, double* scores,
                  int32_t* err_flag, void* stream) {
-  if (!keys || !labels || !pred || !err_flag || B < 0 || k <= 0 || C <= 0 || n_labels <= 0)
-    return fail(B200KNN_E_ARG, "vote: bad argument");
-  if (!(t > 0.0) && !(t < 0.0)) return fail(B200KNN_E_ARG, "vote: temperature must be non-zero");
-  cudaError_t e = b200knn::launch_vote(keys, labels, B, k, n_labels, label_offset, C, t, pred, scores,
-                                       err_flag, static_cast<cudaStream_t>(stream));
-  if (e == cudaErrorInvalidValue) return fail(B200KNN_E_UNSUPPORTED, "vote: k/num_classes too large for shared memory");
-  return e == cudaSuccess ? B200KNN_OK : fail_cuda("vote", e);
+  return b200knn_vote_ex(keys, labels, B, k, n_labels, label_offset, C, t, pred, C, -1, scores, err_flag,
+                         stream);
+}
+
+int b200knn_key_sim_column(const uint64_t* keys, int64_t B, int k, int j, float* out, void* stream) {
+  if (!keys || !out || B < 0 || k <= 0 || j < 0 || j >= k) return fail(B200KNN_E_ARG, "key_sim_column: bad argument");
+  cudaError_t e = b200knn::launch_key_sim_column(keys, B, k, j, out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("key_sim_column", e);
 }
 
 }  // extern "C"

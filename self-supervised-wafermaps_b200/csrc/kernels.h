@@ -31,7 +31,11 @@ cudaError_t launch_decode(const uint64_t* keys, int64_t n, float* sims, int64_t*
                           cudaStream_t stream);
 cudaError_t launch_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
                         int64_t n_labels, int64_t label_offset, int C, double t, int64_t* pred,
-                        double* scores, int32_t* err_flag, cudaStream_t stream);
+                        int64_t pred_ld, int status_col, double* scores, int32_t* err_flag,
+                        cudaStream_t stream);
+// out[b] = similarity of keys[b, j] (-inf for an empty slot)
+cudaError_t launch_key_sim_column(const uint64_t* keys, int64_t B, int k, int j, float* out,
+                                  cudaStream_t stream);
 cudaError_t launch_prepare(const void* src, int src_dtype, int src_layout, int64_t n_vec, int dim,
                            int64_t ld, int mode, void* dst_hi, void* dst_lo, cudaStream_t stream);
 

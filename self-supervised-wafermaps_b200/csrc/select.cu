@@ -77,21 +77,14 @@ __global__ void __launch_bounds__(128) merge_kernel(const uint64_t* __restrict__
         done = push(j0 + lane < k_in ? list[j0 + lane] : 0ull);
     }
   }
-  {
-    uint64_t v[ITEMS];
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < ITEMS; ++r) {
-      const int i = r * 32 + lane;
-      v[r] = i < cnt ? buf[i] : 0ull;
-    }
-    warp_sort_desc<ITEMS>(v, lane);
-#pragma unroll
-    for (int r = 0; r < ITEMS; ++r) {
-      const int i = r * 32 + lane;
-      if (i < k_out) out[row * k_out + i] = v[r];
-    }
-  }
+  // final sort, with the network sized to what survived
+  __syncwarp();
+  uint64_t* o = out + row * k_out;
+  if (cnt <= 64) sort_store<2>(buf, cnt, k_out, lane, o);
+  else if (ITEMS >= 4 && cnt <= 128) sort_store<(ITEMS >= 4 ? 4 : ITEMS)>(buf, cnt, k_out, lane, o);
+  else if (ITEMS >= 8 && cnt <= 256) sort_store<(ITEMS >= 8 ? 8 : ITEMS)>(buf, cnt, k_out, lane, o);
+  else if (ITEMS >= 16 && cnt <= 512) sort_store<(ITEMS >= 16 ? 16 : ITEMS)>(buf, cnt, k_out, lane, o);
+  else sort_store<ITEMS>(buf, cnt, k_out, lane, o);
 }
 
 __global__ void decode_kernel(const uint64_t* __restrict__ keys, int64_t n, float* __restrict__ sims,
@@ -101,6 +94,12 @@ __global__ void decode_kernel(const uint64_t* __restrict__ keys, int64_t n, floa
   const uint64_t key = keys[i];
   if (sims) sims[i] = key_sim(key);
   if (idx) idx[i] = key_idx(key);
+}
+
+__global__ void key_sim_column_kernel(const uint64_t* __restrict__ keys, int64_t B, int k, int j,
+                                      float* __restrict__ out) {
+  const int64_t b = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = key_sim(keys[b * k + j]);
 }
 
 template <int ITEMS>
@@ -128,6 +127,13 @@ cudaError_t launch_merge(const uint64_t* in, int G, int64_t B, int k_in, int k_o
     case 1024: return launch_merge_t<32>(in, G, B, k_in, k_out, out, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launch_key_sim_column(const uint64_t* keys, int64_t B, int k, int j, float* out,
+                                  cudaStream_t stream) {
+  if (B == 0) return cudaSuccess;
+  key_sim_column_kernel<<<unsigned((B + 255) / 256), 256, 0, stream>>>(keys, B, k, j, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const uint64_t* keys, int64_t n, float* sims, int64_t* idx,

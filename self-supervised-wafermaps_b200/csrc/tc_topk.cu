@@ -108,10 +108,11 @@ struct TcKernelArgs {
 // TMA transactions and epilogue arrivals are routed there, and the leader's commits
 // are multicast to both CTAs' smem-empty / TMEM-full / query-empty barriers.
 //
-// SAMPLE: the sampling pre-pass.  Only the kSampleR best SIMILARITIES of every row are
-// wanted (they seed the main pass's admission threshold), so each row's running top-16 lives
-// in its thread's registers (branch-free sorted insert) — no candidate lists, no prunes,
-// no indices.  The general list machinery spent 2/3 of the pre-pass warming up its lists.
+// SAMPLE: the sampling pre-pass.  Only a threshold is wanted: each row's thread keeps the 16
+// best CHUNK MAXIMA (one value per 32 sampled columns) in registers, branch-free sorted
+// insert — no candidate lists, no prunes, no indices.  Its 16-th value is <= the 16-th best
+// sampled similarity, which is all the main pass's admission threshold needs.  The general
+// list machinery spent 2/3 of the pre-pass warming up its lists.
 template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG, bool PAIR, bool SAMPLE>
 __global__ void __launch_bounds__(kThreads, 1)
     tc_topk_kernel(const __grid_constant__ CUtensorMap map_q_hi,
@@ -397,6 +398,23 @@ __global__ void __launch_bounds__(kThreads, 1)
           // ---- some rows of this warp have candidates in this chunk.  Every such row's
           // thread appends its own candidates straight from its registers; rows proceed in
           // parallel, so the cost does not grow with the number of rows that hit.
+          if (SAMPLE) {
+            // Only the chunk maximum of a row is inserted.  The top-16 of a SUBSET of the
+            // sample is still a valid (slightly lower) threshold, a second qualifying value in
+            // the same 32 columns is rare after the first tiles, and the epilogue stays free
+            // of per-column work: 32 min/max per hit, all hit rows in parallel.
+            if (hit) {
+              float x = mx;
+#pragma unroll
+              for (int i = 0; i < kSampleR; ++i) {
+                const float hi = fmaxf(top[i], x);
+                x = fminf(top[i], x);
+                top[i] = hi;
+              }
+              st.tau = top[kSampleR - 1];  // only rows that can hit get here (others hold +inf)
+            }
+            continue;
+          }
           if (hit) {
             // bit j of m: column j qualifies.  Only the column classes (j mod 4) whose partial
             // maximum qualifies are tested; no per-column branches.
@@ -408,44 +426,24 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int j = c; j < 32; j += 4) m |= (s[j] > st.tau) ? (1u << j) : 0u;
               }
             }
-            const bool single = (m & (m - 1u)) == 0u;  // the common case: the row maximum alone
-            if (SAMPLE) {
-              auto insert = [&](float x) {
-#pragma unroll
-                for (int i = 0; i < kSampleR; ++i) {
-                  const float hi = fmaxf(top[i], x);
-                  x = fminf(top[i], x);
-                  top[i] = hi;
-                }
-              };
-              if (single) {
-                insert(mx);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if ((m >> j) & 1u) insert(s[j]);
-              }
-              st.tau = top[kSampleR - 1];  // only rows that can hit get here (others hold +inf)
+            const uint32_t gidx0 = uint32_t(n0 + c0 + a.idx_offset);
+            if ((m & (m - 1u)) == 0u) {
+              // the common case, exactly one candidate: it is the row maximum
+              my_list[st.cnt] = make_key(mx, gidx0 + uint32_t(__ffs(m) - 1));
+              st.cnt += 1;
             } else {
-              const uint32_t gidx0 = uint32_t(n0 + c0 + a.idx_offset);
-              if (single) {
-                my_list[st.cnt] = make_key(mx, gidx0 + uint32_t(__ffs(m) - 1));
-                st.cnt += 1;
-              } else {
-                uint64_t* lp = my_list + st.cnt;
-                uint32_t c = 0;
+              uint64_t* lp = my_list + st.cnt;
+              uint32_t c = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if ((m >> j) & 1u) {
-                    lp[c] = make_key(s[j], gidx0 + uint32_t(j));
-                    ++c;
-                  }
+              for (int j = 0; j < 32; ++j) {
+                if ((m >> j) & 1u) {
+                  lp[c] = make_key(s[j], gidx0 + uint32_t(j));
+                  ++c;
                 }
-                st.cnt += c;
               }
+              st.cnt += c;
             }
           }
-          if (SAMPLE) continue;
           __syncwarp();
           warp_maintain<ITEMS, true>(warp_lists, st, a.k, lane, 32);  // emergency only (list would overflow)
         }

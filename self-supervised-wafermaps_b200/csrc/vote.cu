@@ -20,8 +20,8 @@ constexpr int kVoteWarps = 4;
 __global__ void __launch_bounds__(kVoteWarps * 32)
     vote_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ labels, int64_t B,
                 int k, int64_t n_labels, int64_t label_offset, int C, double t,
-                int64_t* __restrict__ pred, double* __restrict__ scores,
-                int32_t* __restrict__ err_flag) {
+                int64_t* __restrict__ pred, int64_t pred_ld, int status_col,
+                double* __restrict__ scores, int32_t* __restrict__ err_flag) {
   extern __shared__ unsigned char vote_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per warp: w[k] f64 | sc[C] f64 | lab[k] i32
@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kVoteWarps * 32)
   const int64_t row = int64_t(blockIdx.x) * kVoteWarps + warp;
   if (row >= B) return;
 
+  int bad = 0;  // per-row status: 1 empty k-th slot (starved row), 2 label / 4 index out of range
   for (int j = lane; j < k; j += 32) {
     const uint64_t key = keys[row * k + j];
     int l = -1;
@@ -47,13 +48,21 @@ __global__ void __launch_bounds__(kVoteWarps * 32)
           wj = exp(double(key_sim(key)) / t);
         } else {
           atomicExch(err_flag, 1);
+          bad |= 2;
         }
       } else {
         atomicExch(err_flag, 2);
+        bad |= 4;
       }
+    } else if (j == k - 1) {
+      bad |= 1;
     }
     lab[j] = l;
     w[j] = wj;
+  }
+  if (status_col >= 0) {
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0) pred[row * pred_ld + status_col] = bad;
   }
   __syncwarp();
   for (int c = lane; c < C; c += 32) {
@@ -71,7 +80,7 @@ __global__ void __launch_bounds__(kVoteWarps * 32)
       const double so = sc[o];
       rank += (so > s || (so == s && o < c)) ? 1 : 0;
     }
-    pred[row * C + rank] = c;
+    pred[row * pred_ld + rank] = c;
   }
 }
 
@@ -79,7 +88,8 @@ __global__ void __launch_bounds__(kVoteWarps * 32)
 
 cudaError_t launch_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
                         int64_t n_labels, int64_t label_offset, int C, double t, int64_t* pred,
-                        double* scores, int32_t* err_flag, cudaStream_t stream) {
+                        int64_t pred_ld, int status_col, double* scores, int32_t* err_flag,
+                        cudaStream_t stream) {
   if (B == 0) return cudaSuccess;
   const size_t per_warp = (size_t(k) * 8 + size_t(C) * 8 + size_t(k) * 4 + 7) / 8 * 8;
   const size_t smem = per_warp * kVoteWarps;
@@ -91,7 +101,7 @@ cudaError_t launch_vote(const uint64_t* keys, const int64_t* labels, int64_t B, 
   }
   const int64_t blocks = (B + kVoteWarps - 1) / kVoteWarps;
   vote_kernel<<<unsigned(blocks), kVoteWarps * 32, smem, stream>>>(
-      keys, labels, B, k, n_labels, label_offset, C, t, pred, scores, err_flag);
+      keys, labels, B, k, n_labels, label_offset, C, t, pred, pred_ld, status_col, scores, err_flag);
   return cudaGetLastError();
 }
 

@@ -59,8 +59,13 @@ class OracleOps:
         return torch.from_numpy(O.vote_o64(s, i, labels.numpy(), num_classes, knn_t)[0])
 
     @classmethod
-    def vote_flag(cls, keys, labels, num_classes, knn_t):
-        return cls.vote(keys, labels, num_classes, knn_t), torch.zeros(1, dtype=torch.int32)
+    def vote_packed(cls, keys, labels, num_classes, knn_t, n_rows_out):
+        out = torch.zeros((n_rows_out, num_classes + 1), dtype=torch.int64)
+        n = keys.shape[0]
+        if n:
+            out[:n, :num_classes] = cls.vote(keys, labels, num_classes, knn_t)
+            out[:n, num_classes] = (keys[:, -1] == 0).to(torch.int64)
+        return out
 
     @staticmethod
     def decode_keys(keys):
