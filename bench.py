@@ -271,10 +271,25 @@ def main():
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"i": 0, "primed": False}
 
+    # N > 1: every rank uploads only its 1/N slice of the batch over its own PCIe link and the
+    # full batch is assembled with an all-gather over NVLink (every rank needs all queries)
+    q_per = (Q + world - 1) // world
+    q_lo, q_hi = min(Q, rank * q_per), min(Q, (rank + 1) * q_per)
+    if world > 1:
+        slice_host = torch.zeros((q_per, DIM), dtype=q.dtype).pin_memory()
+        slice_host[: q_hi - q_lo] = q_host[q_lo:q_hi]
+        slice_dev = [torch.empty((q_per, DIM), dtype=q.dtype, device=dev) for _ in range(2)]
+        gathered = [torch.empty((q_per * world, DIM), dtype=q.dtype, device=dev) for _ in range(2)]
+        staging = [g[:Q] for g in gathered]
+
     def upload(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
-            staging[slot].copy_(q_host, non_blocking=True)
+            if world > 1:
+                slice_dev[slot].copy_(slice_host, non_blocking=True)
+                dist.all_gather_into_tensor(gathered[slot], slice_dev[slot])
+            else:
+                staging[slot].copy_(q_host, non_blocking=True)
             uploaded[slot].record(copy_stream)
 
     def step_e2e():
@@ -365,7 +380,8 @@ def main():
                        "plan": plan, "bank_prepare_ms_excluded": prepare_ms},
             "roofline": roof,
             "e2e": {"value": Q / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": Q * DIM * 4, "d2h_bytes_per_step": Q * 8,
+                    "h2d_bytes_per_step": Q * DIM * 4, "d2h_bytes_per_step": Q * 8 * world,
+                    "note": "whole-job bytes; N>1: each rank uploads 1/N of the batch, NVLink all-gather assembles it",
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": gpu_launches,
             "clocks": clocks.summary(),

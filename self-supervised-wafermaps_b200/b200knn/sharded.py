@@ -147,10 +147,23 @@ class ShardedBank:
         if sk is None:
             return None
         self._mark("  sample")
-        g = self._gather(sk)
-        self._mark("  gather(B,16)")
-        merged = self.ops.merge_keys(g, sk.shape[1])
-        return self.ops.kth_sim(merged)
+        B, r = sk.shape
+        per, _, _ = self._owned(B)
+        if B < 8 * self.world_size:  # tiny batches: one all-gather, every rank merges every row
+            merged = self.ops.merge_keys(self._gather(sk), r)
+            return self.ops.kth_sim(merged)
+        # by query slice: rank g merges the G sample lists of its own rows only, then the (B,)
+        # thresholds (4 B per query) are all-gathered
+        padded = sk
+        if per * self.world_size != B:
+            padded = torch.zeros((per * self.world_size, r), dtype=sk.dtype, device=sk.device)
+            padded[:B] = sk
+        recv = self._exchange_owned(padded, per)
+        self._mark("  all-to-all(B,16)")
+        tau_own = self.ops.kth_sim(self.ops.merge_keys(recv, r))
+        tau = torch.empty((per * self.world_size,), dtype=tau_own.dtype, device=tau_own.device)
+        dist.all_gather_into_tensor(tau, tau_own.contiguous(), group=self.group)
+        return tau[:B].contiguous()
 
     def topk_keys(self, feature: torch.Tensor, k: int) -> torch.Tensor:
         if k > self.n_rows:

@@ -31,9 +31,18 @@ __global__ void __launch_bounds__(128) merge_kernel(const uint64_t* __restrict__
   const unsigned lt_mask = (1u << lane) - 1u;
   int cnt = 0;
 
-  auto prune = [&]() {  // sort the buffer, keep the best k_out
-    uint64_t v[ITEMS];
+  auto prune = [&]() {  // cut the buffer to ~k_out: radix-select, or sort when ties defeat it
     __syncwarp();
+    if (cnt > k_out) {
+      int kept = -1;
+      warp_prune_select<ITEMS>(buf, cnt, k_out, lane, &kept);
+      __syncwarp();
+      if (kept >= 0) {
+        cnt = kept;
+        return;
+      }
+    }
+    uint64_t v[ITEMS];
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
       const int i = r * 32 + lane;
@@ -77,9 +86,16 @@ __global__ void __launch_bounds__(128) merge_kernel(const uint64_t* __restrict__
         done = push(j0 + lane < k_in ? list[j0 + lane] : 0ull);
     }
   }
-  // final sort, with the network sized to what survived
+  // final sort, with the network sized to what survived (long buffers are first cut to ~k_out
+  // by radix-select, which is several times cheaper than the 512-key network)
   __syncwarp();
   uint64_t* o = out + row * k_out;
+  if (ITEMS > 8 && cnt > 256 && cnt > k_out) {
+    int kept = -1;
+    warp_prune_select<ITEMS>(buf, cnt, k_out, lane, &kept);
+    if (kept >= 0) cnt = kept;
+    __syncwarp();
+  }
   if (cnt <= 64) sort_store<2>(buf, cnt, k_out, lane, o);
   else if (ITEMS >= 4 && cnt <= 128) sort_store<(ITEMS >= 4 ? 4 : ITEMS)>(buf, cnt, k_out, lane, o);
   else if (ITEMS >= 8 && cnt <= 256) sort_store<(ITEMS >= 8 ? 8 : ITEMS)>(buf, cnt, k_out, lane, o);
