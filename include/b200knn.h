@@ -56,6 +56,8 @@ extern "C" {
 #define B200KNN_MODE_BF16 1  /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulate */
 #define B200KNN_MODE_TF32X3 2 /* tcgen05 kind::tf32, hi/lo split operands, 3 MMAs per k-step */
 #define B200KNN_MODE_F32ROWS 3 /* b200knn_prepare_rows only: plain fp32 (n_vec, dim_pad) row-major copy */
+#define B200KNN_MODE_BF16X3 4 /* tcgen05 kind::f16, bf16 hi/lo split operands, 3 MMAs per k-step:
+                                 ~2^-16 relative operand error at twice the TF32X3 MMA rate */
 
 int b200knn_version(void);
 const char* b200knn_last_error(void);
@@ -69,6 +71,7 @@ const char* b200knn_last_error(void);
  *   mode BF16  : dst_hi = (n_vec, dim) bf16 (round-to-nearest-even); dst_lo unused
  *   mode TF32X3: dst_hi = (n_vec, dim) f32 holding tf32-truncated values,
  *                dst_lo = (n_vec, dim) f32 holding  x - hi  (exact)
+ *   mode BF16X3: dst_hi = (n_vec, dim) bf16 = rn(x), dst_lo = (n_vec, dim) bf16 = rn(x - hi)
  */
 int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout,
                          int64_t n_vec, int dim, int64_t ld, int mode,
@@ -80,7 +83,7 @@ int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout,
  *
  *   mode EXACT : q = (B,dim) caller tensor (q_dtype, row-major, ld = q_ld);
  *                bank = caller tensor (bank_dtype, bank_layout, ld = bank_ld)
- *   mode BF16 / TF32X3 : q_hi/q_lo and bank_hi/bank_lo are b200knn_prepare_rows
+ *   mode BF16 / TF32X3 / BF16X3 : q_hi/q_lo and bank_hi/bank_lo are b200knn_prepare_rows
  *                outputs (K-major rows); q_dtype/bank_dtype/layout args ignored.
  *
  * Output: out_keys = (B, k) uint64 selection keys sorted

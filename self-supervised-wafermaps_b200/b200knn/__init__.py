@@ -11,6 +11,8 @@ Public surface (mirrors the reference names for this path):
 from .install import install, uninstall  # noqa: F401
 from .knn import (  # noqa: F401
     ALL_MODES,
+    CASCADES,
+    LEVELS,
     RESCORED_MODES,
     bank_cache,
     decode_keys,

@@ -31,6 +31,8 @@ from . import _lib
 
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
+TC_MODES = ("bf16", "tf32x3", "bf16x3")  # raw tensor-core similarity modes
+
 _default_mode = os.environ.get("B200KNN_MODE", "fp32")
 
 # Measurement hook (bench.py): when set to a list, every b200knn_topk C call is bracketed by
@@ -38,28 +40,48 @@ _default_mode = os.environ.get("B200KNN_MODE", "fp32")
 profile_events = None
 
 
-# "fp32" modes: tensor-core candidate generation + exact re-scoring (csrc/rescore.cu).
-#   candidate mode, extra candidates kept beyond k, error coefficient of the certificate
+# "fp32" modes: tensor-core candidate generation + exact re-scoring (csrc/rescore.cu) + a per-row
+# certificate; uncertified rows fall through to the next level and finally to the exact kernel, so
+# every one of these modes returns bit for bit the "exact" keys.
+#   level: candidate mode, extra candidates kept beyond k, error coefficient of the certificate
 #   (|approx - exact| <= coef * ||q|| * max||bank row||):
-#   tf32x3: 2e-5 is ~10x the largest error observed (dropped lo*lo terms 2^-21, fp32 TMEM
-#           accumulation);  bf16: 2^-8 is the rigorous Cauchy-Schwarz bound of two bf16 roundings.
-RESCORED_MODES = {
-    "fp32": dict(cand="tf32x3", margin=8, err_coef=2e-5),
-    "fp32_bf16": dict(cand="bf16", margin=40, err_coef=2.0 ** -8),
+#   bf16  : 2^-7 is the rigorous Cauchy-Schwarz bound of the two operand roundings (unit roundoff
+#           2^-8 each); +2 % covers their product term and the fp32 accumulation.  The wide margin
+#           (k+128 candidates) is what lets the certificate pass: it needs the exact k-th similarity
+#           to beat the approximate (k+128)-th by 2^-7.
+#   tf32x3: operand error 2^-20 (dropped lo*lo, truncated lo) is rigorous; the fp32 accumulation in
+#           TMEM is not IEEE, so 2e-5 is an EMPIRICAL bound, ~10x the largest error observed.
+#   bf16x3: operands hi + lo with |x - hi - lo| <= 2^-16 |x| each and the dropped lo*lo term
+#           (2^-16): 3 * 2^-16 = 4.6e-5 is rigorous; 6e-5 leaves the same empirical allowance for
+#           the accumulation as tf32x3.
+LEVELS = {
+    "fp32_bf16": dict(cand="bf16", margin=128, err_coef=1.02 * 2.0 ** -7),
+    "fp32_bf16x3": dict(cand="bf16x3", margin=16, err_coef=6e-5),
+    "fp32_tf32": dict(cand="tf32x3", margin=8, err_coef=2e-5),
 }
+# mode -> levels tried in order (then "exact").  "fp32" skips its BF16 level for a bank on which
+# that level recently left more than CASCADE_GIVE_UP of the rows uncertified.
+CASCADES = {"fp32": ("fp32_bf16x3", "fp32_tf32"), "fp32_bf16x3": ("fp32_bf16x3",),
+            "fp32_bf16": ("fp32_bf16",), "fp32_tf32": ("fp32_tf32",)}
+CASCADE_GIVE_UP = 0.25
+CASCADE_RETRY_CALLS = 64
+# first level of each mode (bench / docs)
+RESCORED_MODES = {m: LEVELS[c[0]] for m, c in CASCADES.items()}
 ALL_MODES = tuple(_lib.MODES) + tuple(RESCORED_MODES)
 
 # statistics of the last rescored call (bench / tests): rows that failed the certificate
-last_rescore_stats = {"rows": 0, "uncertified": 0}
+last_rescore_stats = {"rows": 0, "uncertified": 0, "level": None}
 
 
 def set_default_mode(mode: str) -> None:
     """Select the similarity mode ``knn_predict``/``knn_topk`` use when none is passed.
 
     ``"exact"``     fp32 CUDA-core contraction, sequential-fma similarities (bitwise reproducible);
-    ``"fp32"``      tcgen05 3xTF32 candidates + exact re-scoring + certificate: bitwise the
-                    ``"exact"`` result at tensor-core speed (the fp32-matching mode);
-    ``"fp32_bf16"`` same with BF16 candidates (fastest exact mode when neighbours are well separated);
+    ``"fp32"``      tensor-core candidates + exact re-scoring + certificate, cascading split-BF16
+                    (3 MMAs, k+16 candidates) -> 3xTF32 (k+8) -> exact for the rows each level cannot
+                    certify: bitwise the ``"exact"`` result at tensor-core speed (the fp32-matching mode);
+    ``"fp32_bf16x3"`` / ``"fp32_tf32"`` / ``"fp32_bf16"``  a single level (then exact);
+    ``"bf16x3"``    raw tcgen05 bf16 hi/lo-split similarities (~1e-5 relative);
     ``"tf32x3"``    raw tcgen05 hi/lo-split TF32 similarities (fp32-class accuracy, ~1e-6);
     ``"bf16"``      raw tcgen05 BF16 operands / fp32 accumulate (fastest; recall@k reported by bench).
     """
@@ -112,7 +134,7 @@ class PreparedRows:
 
     def rescore_rows(self):
         """(rows_a, rows_b) fp32 row-major operands whose sum is the caller's exact value."""
-        if self.mode == "tf32x3":
+        if self.mode == "tf32x3":  # hi + lo is exactly the caller's fp32 value
             return self.hi, self.lo
         if self._f32 is None:
             src, cols = self._src
@@ -161,6 +183,9 @@ def prepare_rows(x: torch.Tensor, mode: str, vectors_are_columns: bool) -> Prepa
     elif mode == "tf32x3":
         hi = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
         lo = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
+    elif mode == "bf16x3":
+        hi = torch.empty((n, dpad), dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty((n, dpad), dtype=torch.bfloat16, device=x.device)
     elif mode == "f32rows":
         hi = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
         lo = None
@@ -186,6 +211,7 @@ class _BankCache:
     def __init__(self, capacity: int = 4):
         self.capacity = capacity
         self._entries = {}
+        self._state = {}
 
     def get(self, bank: torch.Tensor, mode: str) -> PreparedRows:
         key = (bank.data_ptr(), bank._version, tuple(bank.shape), tuple(bank.stride()), bank.dtype,
@@ -203,8 +229,19 @@ class _BankCache:
         self._entries[key] = (ref, prep)
         return prep
 
+    def state(self, bank: torch.Tensor) -> dict:
+        """Mutable per-bank notes (cascade statistics), dropped with the bank's cache entries."""
+        key = (bank.data_ptr(), bank._version, tuple(bank.shape))
+        st = self._state.get(key)
+        if st is None:
+            if len(self._state) >= 4 * self.capacity:
+                self._state.pop(next(iter(self._state)))
+            st = self._state[key] = {}
+        return st
+
     def clear(self) -> None:
         self._entries.clear()
+        self._state.clear()
 
 
 bank_cache = _BankCache()
@@ -339,7 +376,7 @@ def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode:
     """Pre-pass: (B, r) best keys among every s-th bank row, or None when the pre-pass is off."""
     N = feature_bank.shape[1]
     s = prepass_stride(n_rows_for_decision if n_rows_for_decision is not None else N, k)
-    if s == 0 or mode not in ("bf16", "tf32x3"):
+    if s == 0 or mode not in TC_MODES:
         return None
     B, D = feature.shape
     r = PREPASS["r"]
@@ -451,26 +488,18 @@ def _repair_rows(keys: torch.Tensor, recompute) -> torch.Tensor:
 last_prepass_stats = {"rows": 0, "repaired": 0}
 
 
-def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
-                        idx_offset: int = 0, defer: bool = False):
-    """Tensor-core candidates (k_in = k + margin) -> exact sequential-fma re-scoring -> best k,
-    with a per-row certificate; uncertified rows are recomputed in "exact" mode, so the keys are
-    bitwise those of mode "exact"."""
+def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, level: str, idx_offset: int):
+    """One cascade level, nothing synchronises: (keys (B,k), uncertified flags (B,) int32, count int32[1])."""
     lib = _lib.load()
-    cfg = RESCORED_MODES[mode]
-    _check_feature_bank(feature, feature_bank)
+    cfg = LEVELS[level]
     B, D = feature.shape
     N = feature_bank.shape[1]
-    k = int(k)
-    if k <= 0 or k > N:
-        raise RuntimeError("selected index k out of range")
     k_in = min(N, k + cfg["margin"])
+    if lib.b200knn_topk_workspace_bytes(max(B, 1), N, D, k_in, _lib.MODES[cfg["cand"]]) == 0:
+        k_in = min(N, k + 8)  # k too large for the wide margin's list capacity
     dev = feature.device
-    out = torch.empty((B, k), dtype=torch.int64, device=dev)
-    if B == 0:
-        return out
     # no repair pass on the candidates: a row its sampled threshold starved has an empty k_in-th
-    # slot, which the re-scoring kernel reports as uncertified (-> exact recomputation below)
+    # slot, which the re-scoring kernel reports as uncertified
     cand = topk_keys(feature, feature_bank, k_in, cfg["cand"], idx_offset, repair=False)
     pb = bank_cache.get(feature_bank, cfg["cand"])
     rows_a, rows_b = pb.rescore_rows()
@@ -478,6 +507,7 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
     q = feature if feature.dtype in _DTYPES else feature.float()
     if q.stride(1) != 1:
         q = q.contiguous()
+    out = torch.empty((B, k), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         flags = torch.empty((B,), dtype=torch.int32, device=dev)
         n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
@@ -485,14 +515,75 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
                                        _ptr(rows_b), N, D, cand.data_ptr(), B, k_in, k, idx_offset,
                                        float(cfg["err_coef"]), max_norm.data_ptr(), out.data_ptr(),
                                        flags.data_ptr(), n_bad.data_ptr(), _stream()), "rescore")
-        if defer:  # the caller reads n_bad in its own (single) synchronisation and fixes the rows
-            return out, flags, n_bad
-        bad = int(n_bad.item())
-        last_rescore_stats["rows"] = B
-        last_rescore_stats["uncertified"] = bad
-        if bad:
-            rows = flags.nonzero(as_tuple=False).view(-1)
-            out[rows] = topk_keys(q[rows].contiguous(), feature_bank, k, "exact", idx_offset)
+    return out, flags, n_bad
+
+
+def _cascade_levels(feature_bank: torch.Tensor, mode: str):
+    levels = list(CASCADES[mode])
+    if len(levels) > 1:
+        st = bank_cache.state(feature_bank)
+        if st.get("skip_first", 0) > 0:
+            st["skip_first"] -= 1
+            levels = levels[1:]
+    return levels
+
+
+def _cascade_fix(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, levels, rows: torch.Tensor,
+                 idx_offset: int) -> torch.Tensor:
+    """Keys of `rows` (uncertified at the previous level) from the remaining levels, then exact."""
+    sub = feature[rows].contiguous()
+    for level in levels:
+        out, flags, n_bad = _rescored_level(sub, feature_bank, k, level, idx_offset)
+        if int(n_bad.item()) == 0:
+            return out
+        left = flags.nonzero(as_tuple=False).view(-1)
+        out[left] = _cascade_fix(sub, feature_bank, k, levels[levels.index(level) + 1:], left, idx_offset)
+        return out
+    return topk_keys(sub, feature_bank, k, "exact", idx_offset)
+
+
+def _note_first_level(feature_bank: torch.Tensor, mode: str, levels, rows: int, uncertified: int) -> None:
+    last_rescore_stats["rows"], last_rescore_stats["uncertified"] = rows, uncertified
+    last_rescore_stats["level"] = levels[0]
+    if len(CASCADES[mode]) > 1 and levels[0] == CASCADES[mode][0] and rows > 0 \
+            and uncertified > CASCADE_GIVE_UP * rows:
+        bank_cache.state(feature_bank)["skip_first"] = CASCADE_RETRY_CALLS
+
+
+def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
+                        idx_offset: int = 0, defer: bool = False):
+    """Tensor-core candidates -> exact sequential-fma re-scoring -> best k, with a per-row
+    certificate; rows a level cannot certify go to the next level and finally to the "exact"
+    kernel, so the keys are bitwise those of mode "exact".
+    defer=True: nothing synchronises; returns (keys, flags, n_bad, fix) and the caller, after
+    reading n_bad in its own synchronisation, replaces keys[rows] by fix(rows)."""
+    _check_feature_bank(feature, feature_bank)
+    B, D = feature.shape
+    N = feature_bank.shape[1]
+    k = int(k)
+    if k <= 0 or k > N:
+        raise RuntimeError("selected index k out of range")
+    dev = feature.device
+    if B == 0:
+        out = torch.empty((B, k), dtype=torch.int64, device=dev)
+        return (out, None, None, None) if defer else out
+    levels = _cascade_levels(feature_bank, mode)
+    out, flags, n_bad = _rescored_level(feature, feature_bank, k, levels[0], idx_offset)
+
+    def fix(rows, n_rows_bad):
+        _note_first_level(feature_bank, mode, levels, B, n_rows_bad)
+        if rows is None:
+            return None
+        return _cascade_fix(feature, feature_bank, k, levels[1:], rows, idx_offset)
+
+    if defer:
+        return out, flags, n_bad, fix
+    bad = int(n_bad.item())
+    if bad:
+        rows = flags.nonzero(as_tuple=False).view(-1)
+        out[rows] = fix(rows, bad)
+    else:
+        _note_first_level(feature_bank, mode, levels, B, 0)
     return out
 
 
@@ -581,7 +672,7 @@ def knn_predict(feature: torch.Tensor, feature_bank: torch.Tensor, feature_label
     # sampled threshold starved, or rows whose exact re-scoring could not be certified).
     dev = feature.device
     if mode in RESCORED_MODES:
-        keys, bad_rows, n_bad = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True)
+        keys, bad_rows, n_bad, fix = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True)
         if n_bad is None:  # B == 0
             return vote(keys, feature_labels, num_classes, knn_t)
     else:
@@ -593,13 +684,14 @@ def knn_predict(feature: torch.Tensor, feature_bank: torch.Tensor, feature_label
     pred, flag = vote(keys, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
     status = torch.stack([flag.view(()), n_bad.view(()).to(torch.int32)]).tolist()
     n_fix = int(status[1])
-    if mode in RESCORED_MODES:
-        last_rescore_stats["rows"], last_rescore_stats["uncertified"] = keys.shape[0], n_fix
-    else:
+    if mode not in RESCORED_MODES:
         last_prepass_stats["rows"], last_prepass_stats["repaired"] = keys.shape[0], n_fix
+    elif n_fix == 0:
+        fix(None, 0)  # records the statistics of a fully certified call
     if n_fix:
         rows = bad_rows.nonzero(as_tuple=False).view(-1)
-        fixed = recompute_rows(feature, feature_bank, knn_k, mode, rows)
+        fixed = fix(rows, n_fix) if mode in RESCORED_MODES else \
+            recompute_rows(feature, feature_bank, knn_k, mode, rows)
         pred[rows], flag2 = vote(fixed, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
         status[0] = max(int(status[0]), int(flag2.item()))
     if status[0] == 1:

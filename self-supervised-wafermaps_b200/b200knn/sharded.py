@@ -48,7 +48,7 @@ class _CudaOps:
     def topk_into(feature, bank_shard, k, mode, idx_offset, tau0, out):
         """topk_keys writing into `out` when the mode allows it (tensor-core mode with a threshold)."""
         from .knn import topk_keys
-        if tau0 is not None and mode in ("bf16", "tf32x3"):
+        if tau0 is not None and mode in ("bf16", "tf32x3", "bf16x3"):
             topk_keys(feature, bank_shard, k, mode, idx_offset, tau0, out=out)
         else:
             out.copy_(topk_keys(feature, bank_shard, k, mode, idx_offset, tau0))
@@ -141,7 +141,7 @@ class ShardedBank:
         sample of the WHOLE bank — becomes the same admission threshold on every rank.  Shards
         then only collect rows that can still reach the global top-k, so the per-shard work no
         longer carries a fixed list warm-up (this is what lets the sharded mode scale)."""
-        if self.mode not in ("bf16", "tf32x3") or self.world_size == 1:
+        if self.mode not in ("bf16", "tf32x3", "bf16x3") or self.world_size == 1:
             return None
         sk = self.ops.sample_keys(feature, self.bank_shard, k, self.mode, self.n_rows)
         if sk is None:

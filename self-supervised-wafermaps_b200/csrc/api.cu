@@ -65,10 +65,11 @@ int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout, int64_t
     return fail(B200KNN_E_ARG, "prepare_rows: unknown dtype");
   if (src_layout != B200KNN_LAYOUT_DN && src_layout != B200KNN_LAYOUT_ND)
     return fail(B200KNN_E_ARG, "prepare_rows: unknown layout");
-  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_F32ROWS)
-    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16, TF32X3 or F32ROWS");
-  if (mode == B200KNN_MODE_TF32X3 && !dst_lo)
-    return fail(B200KNN_E_ARG, "prepare_rows: TF32X3 needs dst_lo");
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_F32ROWS &&
+      mode != B200KNN_MODE_BF16X3)
+    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16, TF32X3, BF16X3 or F32ROWS");
+  if ((mode == B200KNN_MODE_TF32X3 || mode == B200KNN_MODE_BF16X3) && !dst_lo)
+    return fail(B200KNN_E_ARG, "prepare_rows: split modes need dst_lo");
   cudaError_t e = b200knn::launch_prepare(src, src_dtype, src_layout, n_vec, dim, ld, mode, dst_hi,
                                           dst_lo, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? B200KNN_OK : fail_cuda("prepare_rows", e);
@@ -131,9 +132,9 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.out = partial;
     e = b200knn::launch_exact(p, plan.grid, plan.cap, st);
     if (e != cudaSuccess) return fail_cuda("topk(exact)", e);
-  } else if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_TF32X3) {
-    if (mode == B200KNN_MODE_TF32X3 && (!q_lo || !bank_lo))
-      return fail(B200KNN_E_ARG, "topk: TF32X3 needs the lo operands");
+  } else if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_TF32X3 || mode == B200KNN_MODE_BF16X3) {
+    if (mode != B200KNN_MODE_BF16 && (!q_lo || !bank_lo))
+      return fail(B200KNN_E_ARG, "topk: split modes need the lo operands");
     b200knn::TcParams p;
     p.mode = mode;
     p.q_hi = q_hi;
@@ -183,7 +184,7 @@ int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo, const void* ba
                     const void* bank_lo, int64_t B, int64_t n_visit, int dim, int k, int64_t idx_offset,
                     int64_t bank_row_stride, const float* tau0, uint64_t* out_keys, void* workspace,
                     size_t workspace_bytes, void* stream) {
-  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3)
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_BF16X3)
     return fail(B200KNN_E_ARG, "topk_ex: tensor-core modes only");
   if (bank_row_stride < 1) return fail(B200KNN_E_ARG, "topk_ex: bank_row_stride must be >= 1");
   return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, k, idx_offset,
@@ -195,7 +196,7 @@ int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo, const void
                         const void* bank_lo, int64_t B, int64_t n_visit, int dim,
                         int64_t bank_row_stride, uint64_t* out_keys, void* workspace,
                         size_t workspace_bytes, void* stream) {
-  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3)
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_BF16X3)
     return fail(B200KNN_E_ARG, "topk_sample: tensor-core modes only");
   if (bank_row_stride < 1) return fail(B200KNN_E_ARG, "topk_sample: bank_row_stride must be >= 1");
   if (n_visit < B200KNN_SAMPLE_R) return fail(B200KNN_E_ARG, "topk_sample: fewer than 16 rows to sample");

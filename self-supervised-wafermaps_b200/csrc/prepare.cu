@@ -9,6 +9,7 @@
 //
 //   MODE_BF16  : dst_hi (n_vec, dim_pad) bf16, round-to-nearest-even
 //   MODE_TF32X3: dst_hi (n_vec, dim_pad) f32 = rna_tf32(x); dst_lo = x - hi
+//   MODE_BF16X3: dst_hi (n_vec, dim_pad) bf16 = rn(x); dst_lo = rn(x - hi)
 //   MODE_F32ROWS: dst_hi (n_vec, dim_pad) f32 = x  (row-major shadow the exact re-scoring gathers)
 // dim_pad = dim rounded up to 64; pad columns are written as zero.
 //
@@ -33,6 +34,10 @@ __device__ __forceinline__ void emit(int mode, float x, void* hi, void* lo, int6
     static_cast<__nv_bfloat16*>(hi)[o] = __float2bfloat16_rn(x);
   } else if (mode == B200KNN_MODE_F32ROWS) {
     static_cast<float*>(hi)[o] = x;
+  } else if (mode == B200KNN_MODE_BF16X3) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    static_cast<__nv_bfloat16*>(hi)[o] = h;
+    static_cast<__nv_bfloat16*>(lo)[o] = __float2bfloat16_rn(x - __bfloat162float(h));
   } else {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));

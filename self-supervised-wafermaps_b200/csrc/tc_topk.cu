@@ -24,6 +24,8 @@
 // 128 x D query tile resident in smem for the whole work item).
 //
 // MODE_BF16  : operands bf16 K-major, kind::f16, UMMA 128 x BLOCK_N x 16.
+// MODE_BF16X3: operands bf16 hi/lo split (prepare.cu), kind::f16; same three products per
+//              k-step as TF32X3 at twice its MMA rate (~2^-16 relative operand error).
 // MODE_TF32X3: operands fp32 hi/lo split (prepare.cu), kind::tf32, UMMA
 //              128 x BLOCK_N x 8; per k-step  hi*lo + lo*hi + hi*hi  accumulate
 //              into the same TMEM tile; A and B are both streamed per k-block.
@@ -119,16 +121,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                    const __grid_constant__ CUtensorMap map_q_lo,
                    const __grid_constant__ CUtensorMap map_b_hi,
                    const __grid_constant__ CUtensorMap map_b_lo, const TcKernelArgs a) {
-  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);
+  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);     // one operand pair, query tile resident
+  constexpr bool kHalf = (MODE != B200KNN_MODE_TF32X3);   // 2-byte elements (kind::f16)
   static_assert(!PAIR || kBf16, "CTA pairs are implemented for the BF16 mode");
   constexpr int CAP = ITEMS * 32;
   constexpr int kCtas = PAIR ? 2 : 1;
   constexpr int kBRows = BLOCK_N / kCtas;  // bank rows of one tile this CTA loads
   constexpr int kBBlockBytes = kBRows * kRowBytes;
   constexpr int kStageBytes = kBf16 ? kBBlockBytes : 2 * (kABlockBytes + kBBlockBytes);
-  constexpr int kElemsPerRow = kBf16 ? 64 : 32;  // elements of one 128-byte k-block row
+  constexpr int kElemsPerRow = kHalf ? 64 : 32;  // elements of one 128-byte k-block row
   constexpr int kUmmaKBytes = 32;                // one MMA consumes 32 bytes of k per row
-  constexpr uint32_t kIdesc = ptx::make_idesc(kBf16 ? 1u : 2u, kTileM * kCtas, BLOCK_N);
+  constexpr uint32_t kIdesc = ptx::make_idesc(kHalf ? 1u : 2u, kTileM * kCtas, BLOCK_N);
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -291,9 +294,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                 for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
                   const uint64_t o = uint64_t((ks * kUmmaKBytes) >> 4);
-                  ptx::umma_tf32(tmem_d, a_hi + o, b_lo + o, kIdesc, uint32_t((kb | ks) != 0));
-                  ptx::umma_tf32(tmem_d, a_lo + o, b_hi + o, kIdesc, 1u);
-                  ptx::umma_tf32(tmem_d, a_hi + o, b_hi + o, kIdesc, 1u);
+                  if (kHalf) {  // BF16X3: bf16 hi/lo split, same three products at the bf16 rate
+                    ptx::umma_f16(tmem_d, a_hi + o, b_lo + o, kIdesc, uint32_t((kb | ks) != 0));
+                    ptx::umma_f16(tmem_d, a_lo + o, b_hi + o, kIdesc, 1u);
+                    ptx::umma_f16(tmem_d, a_hi + o, b_hi + o, kIdesc, 1u);
+                  } else {
+                    ptx::umma_tf32(tmem_d, a_hi + o, b_lo + o, kIdesc, uint32_t((kb | ks) != 0));
+                    ptx::umma_tf32(tmem_d, a_lo + o, b_hi + o, kIdesc, 1u);
+                    ptx::umma_tf32(tmem_d, a_hi + o, b_hi + o, kIdesc, 1u);
+                  }
                 }
               }
               // frees the smem stage (in both CTAs of a pair)
@@ -521,10 +530,11 @@ template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG, bool PAIR, bool SAMPLE =
 cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* dump, int32_t* diag,
                      int flags, const char** why) {
   constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);
+  constexpr bool kHalf = (MODE != B200KNN_MODE_TF32X3);
   constexpr int kCtas = PAIR ? 2 : 1;
   constexpr int kBRows = BLOCK_N / kCtas;
   const int d_pad = (p.D + 63) / 64 * 64;
-  const int elems_per_row = kBf16 ? 64 : 32;
+  const int elems_per_row = kHalf ? 64 : 32;
   TcKernelArgs a;
   a.B = p.B;
   a.N = p.N;
@@ -554,11 +564,11 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   const size_t smem = size_t(fixed) + size_t(stages) * stage_bytes;
 
   CUtensorMap mq_hi, mq_lo, mb_hi, mb_lo;
-  bool ok = make_map(&mq_hi, p.q_hi, kBf16, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-            make_map(&mb_hi, p.bank_hi, kBf16, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
+  bool ok = make_map(&mq_hi, p.q_hi, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
+            make_map(&mb_hi, p.bank_hi, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
   if (ok && !kBf16)
-    ok = make_map(&mq_lo, p.q_lo, false, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-         make_map(&mb_lo, p.bank_lo, false, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
+    ok = make_map(&mq_lo, p.q_lo, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
+         make_map(&mb_lo, p.bank_lo, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
   if (!ok) {
     *why = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
@@ -620,6 +630,8 @@ cudaError_t launch_mode(const TcParams& p, int grid, int cap, cudaStream_t strea
   }
   if (p.mode == B200KNN_MODE_TF32X3)
     return launch_cap<B200KNN_MODE_TF32X3, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
+  if (p.mode == B200KNN_MODE_BF16X3)
+    return launch_cap<B200KNN_MODE_BF16X3, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
   *why = "unknown mode";
   return cudaErrorNotSupported;
 }

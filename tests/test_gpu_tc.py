@@ -55,7 +55,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3"])
 @pytest.mark.parametrize("name,_", CASES)
 def test_tiles_and_selection(name, _, mode):
     c = datagen.make_case(name)
@@ -68,6 +68,14 @@ def test_tiles_and_selection(name, _, mode):
         bh = pb.hi.float().cpu().numpy()[:, :D].astype(np.float64)
         ref = qh @ bh.T
         tol = 2e-6  # fp32 accumulation of exact bf16 products
+    elif mode == "bf16x3":
+        # hi + lo carries 16 mantissa bits: |x - hi - lo| <= 2^-16 |x|; the kernel drops lo*lo
+        qf = (pq.hi.double() + pq.lo.double()).cpu().numpy()[:, :D]
+        bf = (pb.hi.double() + pb.lo.double()).cpu().numpy()[:, :D]
+        assert np.abs(qf - q).max() <= 2.0 ** -16 * np.abs(q).max() * 1.01
+        ref = q.astype(np.float64) @ bank.astype(np.float64)
+        scale = np.linalg.norm(q, axis=1).max() * np.linalg.norm(bank, axis=0).max()
+        tol = 6e-5 * max(scale, 1e-30)  # the certificate coefficient of level fp32_bf16x3
     else:
         qf = (pq.hi.double() + pq.lo.double()).cpu().numpy()[:, :D]
         bf = (pb.hi.double() + pb.lo.double()).cpu().numpy()[:, :D]
@@ -98,7 +106,7 @@ def test_tf32x3_raw_accuracy(name):
     assert r["recall_at_k"] >= 0.999
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
 @pytest.mark.parametrize("name", datagen.CASE_NAMES)
 def test_fp32_modes_bitwise_equal_exact_and_oracle(name, mode):
     """The fp32-matching modes (tensor-core candidates + exact re-scoring + certificate) must give
@@ -118,12 +126,12 @@ def test_fp32_modes_bitwise_equal_exact_and_oracle(name, mode):
     finally:
         b200knn.set_default_mode("exact")
     assert np.array_equal(pred, O.vote_o64(ss, si, c["labels"], c["C"], c["t"])[0])
-    print(f"{mode} {name}: uncertified rows {stats['uncertified']}/{stats['rows']}")
-    if mode == "fp32":
+    print(f"{mode} {name}: first level {stats['level']}, uncertified rows {stats['uncertified']}/{stats['rows']}")
+    if mode == "fp32_tf32":
         assert stats["uncertified"] <= max(1, stats["rows"] // 10)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
 @pytest.mark.parametrize("model", ["FastSiam", "SimSiam"])
 def test_fp32_modes_real_banks(model, mode, golden_dir):
     """Duplicates, 80 % exact zeros, row norms up to 277 (un-normalised): certificate + fallback
@@ -155,7 +163,7 @@ def test_bf16_recall(name):
     assert r["recall_at_k"] >= 0.98 and r["max_rel_err"] <= 2e-2
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "fp32", "fp32_bf16"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3", "fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
 def test_large_bank_against_exact_mode(mode):
     """Sizes the CPU oracle cannot cover: tensor-core modes against the on-device exact mode
     (itself bit-checked against the oracle in test_gpu_exact.py) on a 811,457 x 512 bank."""
@@ -170,11 +178,11 @@ def test_large_bank_against_exact_mode(mode):
     ei, ti = ei.cpu().numpy(), ti.cpu().numpy()
     recall = np.mean([len(set(ei[b]) & set(ti[b])) / k for b in range(B)])
     print(f"{mode} recall@{k} vs exact at N={N}: {recall:.5f}")
-    if mode in ("fp32", "fp32_bf16"):
+    if mode in ("fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"):
         print(f"   uncertified rows {K.last_rescore_stats['uncertified']}/{K.last_rescore_stats['rows']}")
         assert torch.equal(ek, tk)  # bitwise: indices, similarities, order
-    elif mode == "tf32x3":
-        assert recall >= 0.9995 and float((es - ts).abs().max()) <= 1e-5
+    elif mode in ("tf32x3", "bf16x3"):
+        assert recall >= (0.9995 if mode == "tf32x3" else 0.998) and float((es - ts).abs().max()) <= (1e-5 if mode == "tf32x3" else 6e-5)
         # batch invariance of the tensor-core path: same rows, smaller batch, identical keys
         tk2 = b200knn.topk_keys(q[:64].contiguous(), bank, k, mode=mode)
         assert torch.equal(tk2, tk[:64])
@@ -182,7 +190,7 @@ def test_large_bank_against_exact_mode(mode):
         assert recall >= 0.98
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3"])
 def test_prepass_threshold_does_not_change_results(mode):
     """The sampling pre-pass only supplies a starting threshold: keys with it on and off must be
     bitwise identical (and the repair path must be a no-op or fix every row)."""
