@@ -138,6 +138,28 @@ int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo,
                         void* stream);
 
 /*
+ * Fused similarity + top-k + exchange for the bank-row-sharded mode (no counterpart in the
+ * reference): b200knn_topk_ex whose result rows are not returned locally but stored, as each
+ * query tile finishes, straight into the exchange buffer of the GPU that owns that query —
+ * peer memory over NVLink, so the all-to-all of candidate keys overlaps the remaining tiles'
+ * math instead of following the kernel.
+ *   host_peer_out : HOST array of n_peers DEVICE pointers; peer g's buffer is
+ *                   (n_peers, rows_per_owner, k) uint64 and must be mapped in this process
+ *                   (symmetric / IPC memory with peer access enabled);
+ *   query row b   : owner = b / rows_per_owner; keys go to
+ *                   peer_out[owner][my_rank][b - owner*rows_per_owner][0..k)
+ * After a cross-GPU barrier every GPU holds, for its own query rows, all shards' sorted
+ * lists in b200knn_merge's input layout.  Only problems planned without bank splits
+ * (b200knn_plan_info splits == 1) are supported; others return B200KNN_E_UNSUPPORTED.
+ */
+int b200knn_topk_scatter(int mode, const void* q_hi, const void* q_lo,
+                         const void* bank_hi, const void* bank_lo, int64_t B, int64_t N,
+                         int dim, int k, int64_t idx_offset, const float* tau0,
+                         const void* const* host_peer_out, int n_peers, int my_rank,
+                         int64_t rows_per_owner, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/*
  * Merge G sorted candidate lists per query into one (replaces nothing in the
  * reference; it is the exchange step of the bank-row-sharded mode, applied to
  * the buffer an all-gather of per-shard b200knn_topk outputs produces).

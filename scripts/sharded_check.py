@@ -15,7 +15,8 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
-for (N, D, B, k, C) in [(200000, 512, 300, 200, 9), (30000, 512, 130, 20, 38), (50001, 384, 65, 5, 9)]:
+for (N, D, B, k, C) in [(200000, 512, 300, 200, 9), (30000, 512, 130, 20, 38), (50001, 384, 65, 5, 9),
+                        (120001, 512, 19001, 200, 9)]:  # the last one is large enough for the fused exchange
     g = torch.Generator(device=dev).manual_seed(811)  # same seed on every rank -> replicated inputs
     bank = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device=dev), dim=1).t().contiguous()
     q = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device=dev), dim=1)
@@ -29,6 +30,10 @@ for (N, D, B, k, C) in [(200000, 512, 300, 200, 9), (30000, 512, 130, 20, 38), (
         p2 = sb.knn_predict(q, C, k, 0.1)                        # all-to-all by query slice (default)
         p3 = sb.knn_predict(q, C, k, 0.1, exchange="allgather")  # the literal all-gather of keys
         assert torch.equal(p2, p3), "exchange variants disagree"
+        b200knn.ShardedBank.fused_exchange = False                 # NCCL all-to-all instead of P2P stores
+        p4 = sb.knn_predict(q, C, k, 0.1)
+        b200knn.ShardedBank.fused_exchange = True
+        assert torch.equal(p2, p4), "fused (P2P) and NCCL exchanges disagree"
         # bf16: per-shard similarities are bitwise those of the unsharded run as well (fixed-order
         # accumulation, no split-K), so even the approximate mode is shard-count invariant
         same = bool(torch.equal(single, sharded)) and bool(torch.equal(p1, p2))

@@ -46,6 +46,11 @@ SIGNATURES = {
         [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64,
          c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "b200knn_topk_scatter": (
+        c_int,
+        [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_void_p,
+         ctypes.POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_size_t, c_void_p],
+    ),
     "b200knn_merge": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "b200knn_decode_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "b200knn_vote": (
@@ -78,7 +83,7 @@ _lib = None
 # kernels each C entry point launches (bench.py's gpu_launches; a b200knn_topk* call whose plan
 # splits the bank launches one more, the split merge — bench.py adds those from plan_info)
 KERNELS_PER_CALL = {
-    "b200knn_prepare_rows": 1, "b200knn_topk": 1, "b200knn_topk_ex": 1, "b200knn_topk_sample": 1,
+    "b200knn_prepare_rows": 1, "b200knn_topk": 1, "b200knn_topk_ex": 1, "b200knn_topk_sample": 1, "b200knn_topk_scatter": 1,
     "b200knn_merge": 1, "b200knn_decode_keys": 1, "b200knn_vote": 1, "b200knn_vote_ex": 1,
     "b200knn_key_sim_column": 1, "b200knn_rescore": 1,
     "b200knn_row_norm_max": 1, "b200knn_debug_topk_dump": 1,

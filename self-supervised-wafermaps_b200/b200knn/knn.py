@@ -454,6 +454,47 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
                                                         idx_offset, 1, None, dev))
 
 
+def topk_scatter(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str, idx_offset: int,
+                 tau0: Optional[torch.Tensor], peer_ptrs, rank: int, rows_per_owner: int) -> bool:
+    """Fused top-k + exchange (b200knn_topk_scatter): this shard's keys of query row b are stored
+    into peer_ptrs[b // rows_per_owner] (device pointers of every rank's (G, rows_per_owner, k)
+    exchange buffer, mapped in this process).  Returns False when the problem is planned with
+    bank splits (caller falls back to the NCCL exchange)."""
+    lib = _lib.load()
+    if mode not in TC_MODES:
+        return False
+    _check_feature_bank(feature, feature_bank)
+    B, D = feature.shape
+    N = feature_bank.shape[1]
+    G = len(peer_ptrs)
+    if B == 0 or k > N or G > 8:
+        return False
+    if plan_info(B, N, D, k, mode)["splits"] != 1:
+        return False
+    dev = feature.device
+    with torch.cuda.device(dev):
+        pb = bank_cache.get(feature_bank, mode)
+        pq = query_cache.get(feature, mode)
+        ws_bytes = lib.b200knn_topk_workspace_bytes(B, N, D, k, _lib.MODES[mode])
+        if ws_bytes == 0:
+            return False
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        ptrs = (ctypes.c_void_p * G)(*[int(p) for p in peer_ptrs])
+        ev = None
+        if profile_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        rc = lib.b200knn_topk_scatter(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(),
+                                      _ptr(pb.lo), B, N, D, k, idx_offset,
+                                      _ptr(None if tau0 is None else tau0.contiguous()), ptrs, G, rank,
+                                      rows_per_owner, ws.data_ptr(), ws_bytes, _stream())
+        if ev is not None:
+            ev[1].record()
+            profile_events.append(ev)
+        _lib.check(rc, "topk_scatter")
+    return True
+
+
 def recompute_rows(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str, rows: torch.Tensor,
                    idx_offset: int = 0) -> torch.Tensor:
     """Keys of the given query rows computed without any admission threshold."""

@@ -22,6 +22,7 @@ no CPU implementation in the product.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -52,6 +53,19 @@ class _CudaOps:
             topk_keys(feature, bank_shard, k, mode, idx_offset, tau0, out=out)
         else:
             out.copy_(topk_keys(feature, bank_shard, k, mode, idx_offset, tau0))
+
+    @staticmethod
+    def scatter_supported(B, n_rows, D, k, mode):
+        from .knn import plan_info
+        try:
+            return plan_info(B, n_rows, D, k, mode)["splits"] == 1
+        except RuntimeError:
+            return False
+
+    @staticmethod
+    def topk_scatter(feature, bank_shard, k, mode, idx_offset, tau0, peer_ptrs, rank, rows_per_owner):
+        from .knn import topk_scatter
+        return topk_scatter(feature, bank_shard, k, mode, idx_offset, tau0, peer_ptrs, rank, rows_per_owner)
 
     @staticmethod
     def sample_keys(feature, bank_shard, k, mode, n_rows_global):
@@ -108,6 +122,7 @@ class ShardedBank:
         self.labels = labels
         self.mode = mode
         self.ops = ops or _CudaOps
+        self._symm = {}
 
     @classmethod
     def from_full(cls, feature_bank: torch.Tensor, labels: torch.Tensor, **kw) -> "ShardedBank":
@@ -207,6 +222,52 @@ class ShardedBank:
         dist.all_to_all_single(recv, local_padded, group=self.group)
         return recv.view(self.world_size, per, local_padded.shape[1])
 
+    # ------------------------------------------------------------------ fused exchange (NVLink P2P)
+    fused_exchange = os.environ.get("B200KNN_FUSED_EXCHANGE", "1") == "1"
+
+    def _symmetric_buffer(self, per: int, k: int, device):
+        """(G, per, k) int64 exchange buffer in symmetric memory + its rendezvous handle (every
+        rank's copy is mapped into every process: handle.buffer_ptrs), cached per shape."""
+        key = (per, k)
+        hit = self._symm.get(key)
+        if hit is None:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty((self.world_size, per, k), dtype=torch.int64, device=device)
+            buf.zero_()  # rows past B are never written: they must read as empty lists
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            hit = self._symm[key] = (buf, hdl)
+        return hit
+
+    def _owned_keys_fused(self, feature: torch.Tensor, k: int, tau0, per: int) -> Optional[torch.Tensor]:
+        """The compute step and its collective as ONE kernel: every shard's tc_topk kernel stores the
+        keys of each query tile it finishes into the owner GPU's exchange buffer over NVLink, so the
+        all-to-all overlaps the remaining tiles' math.  Returns None when not applicable."""
+        if not (self.fused_exchange and feature.is_cuda and hasattr(self.ops, "topk_scatter")):
+            return None
+        if self.world_size > 8 or self.mode not in ("bf16", "tf32x3", "bf16x3"):
+            return None
+        # the decision must be the same on every rank: check every shard's size and work plan
+        B, D = feature.shape
+        for r in range(self.world_size):
+            lo, hi = shard_bounds(self.n_rows, self.world_size, r)
+            if hi - lo < k or not self.ops.scatter_supported(B, hi - lo, D, k, self.mode):
+                return None
+        try:
+            buf, hdl = self._symmetric_buffer(per, k, feature.device)
+        except Exception:  # symmetric memory unavailable on this system: NCCL exchange instead
+            type(self).fused_exchange = False
+            return None
+        hdl.barrier(channel=0)  # every rank is done reading its buffer of the previous call
+        ok = self.ops.topk_scatter(feature, self.bank_shard, k, self.mode, self.lo, tau0,
+                                   list(hdl.buffer_ptrs), self.rank, per)
+        self._mark("  local topk + scatter")
+        hdl.barrier(channel=1)  # every rank's stores have landed
+        if not ok:
+            raise RuntimeError("b200knn: fused exchange refused after the collective decision to use it")
+        self._mark("  barrier")
+        return self.ops.merge_keys(buf, k)
+
     def owned_keys(self, feature: torch.Tensor, k: int, tau0: Optional[torch.Tensor]) -> torch.Tensor:
         """Merged global top-k keys of the query rows this rank owns: (per, k); rows past B and
         slots a too-high threshold starved are empty (0)."""
@@ -214,6 +275,10 @@ class ShardedBank:
         per, _, _ = self._owned(B)
         rows = self.hi - self.lo
         k_loc = min(k, rows)
+        if B > 0:
+            fused = self._owned_keys_fused(feature, k, tau0, per)
+            if fused is not None:
+                return fused
         if k_loc == k and B > 0 and hasattr(self.ops, "topk_into"):
             # the kernel writes its keys straight into the exchange buffer; only the pad rows are zeroed
             local = torch.empty((per * self.world_size, k), dtype=torch.int64, device=feature.device)

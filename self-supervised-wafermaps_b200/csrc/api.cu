@@ -86,15 +86,20 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
                      int64_t bank_ld, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
                      uint64_t* out_keys, void* workspace, size_t workspace_bytes, void* stream,
                      float* dump, int32_t* diag, int flags, int64_t bank_row_stride = 1,
-                     const float* tau0 = nullptr, bool sample = false) {
+                     const float* tau0 = nullptr, bool sample = false,
+                     const void* const* host_peer_out = nullptr, int n_peers = 0, int my_rank = 0,
+                     int64_t rows_per_owner = 0) {
   if (B < 0 || N <= 0 || dim <= 0) return fail(B200KNN_E_ARG, "topk: bad shape");
   if (k <= 0 || k > N) return fail(B200KNN_E_ARG, "topk: selected index k out of range");
   if (N + idx_offset >= 0xFFFFFFFFll || idx_offset < 0)
     return fail(B200KNN_E_ARG, "topk: bank index does not fit 32 bits");
   if (B == 0) return B200KNN_OK;
-  if (!q_hi || !bank_hi || !out_keys || !workspace) return fail(B200KNN_E_ARG, "topk: null pointer");
+  if (!q_hi || !bank_hi || (!out_keys && n_peers == 0) || !workspace)
+    return fail(B200KNN_E_ARG, "topk: null pointer");
   b200knn::TopkPlan plan;
   if (!plan_for(mode, B, N, dim, k, &plan)) return fail(B200KNN_E_UNSUPPORTED, "topk: k too large (max 992)");
+  if (n_peers > 0 && plan.splits > 1)
+    return fail(B200KNN_E_UNSUPPORTED, "topk_scatter: this problem is planned with bank splits; use topk_ex");
   uintptr_t ws = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
   const size_t slack = ws - reinterpret_cast<uintptr_t>(workspace);
   if (workspace_bytes < plan.total_bytes + slack) return fail(B200KNN_E_WORKSPACE, "topk: workspace too small");
@@ -154,6 +159,11 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.bank_row_stride = bank_row_stride;
     p.tau0 = tau0;
     p.sample = sample;
+    p.n_peers = n_peers;
+    p.my_rank = my_rank;
+    p.rows_per_owner = rows_per_owner;
+    for (int g = 0; g < n_peers; ++g)
+      p.peer_out[g] = static_cast<uint64_t*>(const_cast<void*>(host_peer_out[g]));
     const char* why = "";
     e = b200knn::launch_tc(p, plan.grid, plan.cap, st, dump, diag, flags, &why);
     if (e == cudaErrorNotSupported) return fail(B200KNN_E_UNSUPPORTED, "topk(tc): %s", why);
@@ -203,6 +213,23 @@ int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo, const void
   return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, B200KNN_SAMPLE_R, 0,
                    out_keys, workspace, workspace_bytes, stream, nullptr, nullptr, 0, bank_row_stride,
                    nullptr, true);
+}
+
+int b200knn_topk_scatter(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
+                         const void* bank_lo, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
+                         const float* tau0, const void* const* host_peer_out, int n_peers, int my_rank,
+                         int64_t rows_per_owner, void* workspace, size_t workspace_bytes, void* stream) {
+  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_BF16X3)
+    return fail(B200KNN_E_ARG, "topk_scatter: tensor-core modes only");
+  if (!host_peer_out || n_peers < 1 || n_peers > 8 || my_rank < 0 || my_rank >= n_peers)
+    return fail(B200KNN_E_ARG, "topk_scatter: 1..8 peers and a rank among them");
+  if (rows_per_owner <= 0 || rows_per_owner * n_peers < B)
+    return fail(B200KNN_E_ARG, "topk_scatter: rows_per_owner * n_peers must cover B");
+  for (int g = 0; g < n_peers; ++g)
+    if (!host_peer_out[g]) return fail(B200KNN_E_ARG, "topk_scatter: null peer buffer");
+  return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, N, dim, k, idx_offset, nullptr,
+                   workspace, workspace_bytes, stream, nullptr, nullptr, 0, 1, tau0, false,
+                   host_peer_out, n_peers, my_rank, rows_per_owner);
 }
 
 // Test hook (not part of the product path): same as b200knn_topk for the tensor-core

@@ -243,20 +243,21 @@ __device__ __forceinline__ void sort_store(const uint64_t* list, int n, int k, i
 }
 
 // End of a work item: every row of the warp is pruned one last time and its
-// best k keys (sorted descending, zero-padded) are written to `out` (row r of
-// the warp at out + r*out_stride) if row_valid.  The sorting network is sized to
+// best k keys (sorted descending, zero-padded) are written out if row_valid.  The sorting network is sized to
 // the row's candidate count (rows that ran under a good threshold hold few), and
 // long lists are first cut to ~k by radix-select.
-template <int ITEMS>
+// `out_of(r)` returns where row r of the warp goes (a local buffer, or a peer GPU's exchange
+// buffer when the kernel scatters its results over NVLink).
+template <int ITEMS, typename OutFn>
 __device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, int k, int lane,
-                                           uint64_t* out, size_t out_stride, unsigned valid_mask) {
+                                           unsigned valid_mask, OutFn out_of) {
   constexpr int CAP = ITEMS * 32;
   __syncwarp();
   for (int src = 0; src < 32; ++src) {
     if (!((valid_mask >> src) & 1u)) continue;
     int n_valid = __shfl_sync(kFull, int(st.cnt), src);
     uint64_t* list = lists + size_t(src) * CAP;
-    uint64_t* o = out + size_t(src) * out_stride;
+    uint64_t* o = out_of(src);
     if (ITEMS > 8 && n_valid > 256 && n_valid > k) {
       int kept = -1;
       warp_prune_select<ITEMS>(list, n_valid, k, lane, &kept);

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(ExactParams p) {
         valid = nv >= 32 ? kFull : ((1u << nv) - 1u);
       }
       uint64_t* out = p.out + (size_t(sp) * p.B + row0) * p.k;
-      warp_flush<ITEMS>(warp_lists, st, p.k, lane, out, size_t(p.k), valid);
+      warp_flush<ITEMS>(warp_lists, st, p.k, lane, valid,
+                        [&](int r) { return out + size_t(r) * size_t(p.k); });
     }
     __syncthreads();
   }

@@ -77,6 +77,10 @@ struct TcParams {
   uint64_t* out;  // (splits, B, k)
   int64_t bank_row_stride = 1;  // visit every bank_row_stride-th prepared row (sampling pre-pass)
   const float* tau0 = nullptr;  // optional (B,) initial admission thresholds
+  // fused exchange: scatter each query row's keys into its owner GPU's buffer (peer memory)
+  uint64_t* peer_out[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_peers = 0, my_rank = 0;
+  int64_t rows_per_owner = 0;
   bool sample = false;  // sampling pre-pass: k == 16 best SIMILARITIES per row (keys carry index 0)
 };
 // returns cudaErrorNotSupported if (D, k) is outside what the kernel handles

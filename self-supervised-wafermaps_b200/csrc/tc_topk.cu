@@ -71,6 +71,7 @@ constexpr int kEpiWarps = 4 * kEpiPerQuarter;
 constexpr int kRowsPerWarp = 32 / kEpiPerQuarter;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemLimit = 232448;  // 227 KB
+constexpr int kMaxPeers = 8;        // GPUs of one NVSwitch domain the fused exchange addresses
 constexpr int kSampleR = 16;        // values kept per row by the SAMPLE variant (= its k)
 
 struct alignas(16) Barriers {
@@ -94,6 +95,12 @@ struct TcKernelArgs {
   uint64_t* lists;
   uint64_t* out;
   const float* tau0;  // optional (B,) initial admission thresholds (nullptr: -inf)
+  // Fused exchange (sharded mode): when n_peers > 0 the finished keys of query row g are stored
+  // straight into the exchange buffer of the GPU that owns that query (peer memory over
+  // NVLink), at [my_rank][g - owner*rows_per_owner][:], instead of into `out`.
+  uint64_t* peer_out[kMaxPeers];
+  int n_peers, my_rank;
+  int64_t rows_per_owner;
   float* dump;  // optional (B, N) fp32 similarity dump for unit tests (nullptr in production)
   int32_t* diag;
   int flags;    // experiment switches of the debug entry point (0 in production):
@@ -476,8 +483,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         valid = nv >= 32 ? kFull : ((1u << nv) - 1u);
       }
       valid &= (kRowsPerWarp == 32 ? kFull : ((1u << kRowsPerWarp) - 1u)) << (sub * kRowsPerWarp);
-      uint64_t* out = a.out + (size_t(sp) * a.B + row0) * a.k;
-      warp_flush<ITEMS>(warp_lists, st, a.k, lane, out, size_t(a.k), valid);
+      warp_flush<ITEMS>(warp_lists, st, a.k, lane, valid, [&](int r) -> uint64_t* {
+        const int64_t g = row0 + r;
+        if (a.n_peers > 0) {
+          const int64_t owner = g / a.rows_per_owner;
+          return a.peer_out[owner] +
+                 (int64_t(a.my_rank) * a.rows_per_owner + (g - owner * a.rows_per_owner)) * a.k;
+        }
+        return a.out + (size_t(sp) * a.B + size_t(g)) * a.k;
+      });
     }
   }
 
@@ -547,6 +561,10 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   a.lists = p.lists;
   a.out = p.out;
   a.tau0 = p.tau0;
+  a.n_peers = p.n_peers;
+  a.my_rank = p.my_rank;
+  a.rows_per_owner = p.rows_per_owner;
+  for (int g = 0; g < kMaxPeers; ++g) a.peer_out[g] = g < p.n_peers ? p.peer_out[g] : nullptr;
   a.dump = dump;
   a.diag = diag;
   a.flags = flags;
