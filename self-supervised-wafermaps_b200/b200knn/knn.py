@@ -32,6 +32,7 @@ from . import _lib
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
 TC_MODES = ("bf16", "tf32x3", "bf16x3")  # raw tensor-core similarity modes
+MAX_BF16_DIM = 768  # widest (padded) vector whose query tile the BF16 kernel can keep resident
 
 _default_mode = os.environ.get("B200KNN_MODE", "fp32")
 
@@ -408,6 +409,10 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
         raise ValueError(f"unknown mode {mode!r}")
     _check_feature_bank(feature, feature_bank)
     B, D = feature.shape
+    if mode == "bf16" and padded_dim(D) > MAX_BF16_DIM:
+        # the BF16 kernel keeps a 128-row query tile resident in shared memory (D_pad * 256 B);
+        # wider vectors go through the split kernel, which streams both operands
+        mode = "bf16x3"
     N = feature_bank.shape[1]
     k = int(k)
     if k <= 0 or k > N:
