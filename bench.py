@@ -79,32 +79,40 @@ def make_inputs(device, n_bank, n_query, dim, seed):
 
 
 class ClockSampler:
+    """Samples SM clocks and throttle reasons with one streaming `nvidia-smi -lms 50` process
+    while the timed region runs (a fresh nvidia-smi per sample is too slow for sub-second runs)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
     def __init__(self, index=0):
-        self.rows, self.stop = [], threading.Event()
-        self.index = index
+        self.rows, self.index, self.proc = [], index, None
         self.th = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
                 if len(parts) >= 6:
                     self.rows.append(parts)
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        except Exception:
+            pass
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.15)  # let the first sample land before the timed region starts
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.th.join(timeout=6)
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        self.th.join(timeout=3)
 
     def summary(self):
         if not self.rows:
@@ -177,7 +185,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", default=os.environ.get("B200KNN_BENCH_MODE", "bf16"))

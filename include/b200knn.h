@@ -234,6 +234,28 @@ int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_
                     uint64_t* out_keys, int32_t* uncertified,
                     int32_t* n_uncertified, void* stream);
 
+/*
+ * SURVEY.md §8(f) rows — the steps either side of knn_predict in the reference.
+ *
+ * b200knn_normalize_rows: F.normalize(x, dim=1) of n_vec row vectors (reference
+ * src/ssl_wafermap/models/knn.py:77 bank rows, :90 queries) fused with the relayout into the
+ * padded (n_vec, dim_pad) fp32 rows the kernels read; y = x / max(||x||_2, eps).  The norm is
+ * accumulated in fp64 in a fixed order (see csrc/prepare.cu), so the result is reproducible.
+ *
+ * b200knn_confusion: counts[t*C + p] += #(target == t, pred == p) — the confusion matrix of
+ * src/ssl_wafermap/models/knn.py:121-127; macro accuracy / F1 follow from it.  err_flag is
+ * set to 1 if a prediction or target lies outside [0, C).  C <= 64.
+ */
+int b200knn_normalize_rows(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld,
+                           float eps, float* dst_rows, void* stream);
+/* out[n] = float(sum_d x[n,d]^2) with the accumulation order of b200knn_normalize_rows: the
+ * ||x||^2 column that turns a dot-product top-k into the L2 ranking of
+ * notebooks/2.0-Figures-nearest-neighbors.ipynb:54 (argmin ||x-q|| = argmax 2 q.x - ||x||^2). */
+int b200knn_row_sqnorms(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld,
+                        float* out, void* stream);
+int b200knn_confusion(const int64_t* pred, const int64_t* target, int64_t n, int C,
+                      int64_t* counts, int32_t* err_flag, void* stream);
+
 /* Device capability probe for the host shim: 1 if the current device is sm_100. */
 int b200knn_device_ok(void);
 

@@ -285,3 +285,69 @@ def compare_pred(got_pred: np.ndarray, scores64: np.ndarray, rel_margin: float =
         "rank_mismatch_unambiguous": float((~eq & unamb).sum()),
         "rank_mismatch_total": float((~eq).sum()),
     }
+
+
+# --------------------------------------------------------------------------- §8(f) rows
+def _sqnorm_f64_lane_order(x32: np.ndarray) -> np.ndarray:
+    """sum_d x^2 per row in the accumulation order of csrc/prepare.cu (normalize_rows_kernel /
+    row_sqnorm_kernel): lane l adds columns l, l+32, ... sequentially in fp64, then an xor
+    butterfly (16, 8, 4, 2, 1) combines the 32 partials."""
+    x = np.asarray(x32, dtype=np.float32).astype(np.float64)
+    n, d = x.shape
+    part = np.zeros((n, 32), dtype=np.float64)
+    for d0 in range(0, d, 32):
+        blk = x[:, d0:d0 + 32]
+        part[:, : blk.shape[1]] += blk * blk  # one rounding per add; the square is exact
+    lanes = np.arange(32)
+    for o in (16, 8, 4, 2, 1):
+        part = part + part[:, lanes ^ o]
+    return part[:, 0]
+
+
+def normalize_rows_ref(x: np.ndarray, eps: float = 1e-12) -> np.ndarray:
+    """F.normalize(x, dim=1) (reference src/ssl_wafermap/models/knn.py:77, :90) with the fixed
+    arithmetic of b200knn_normalize_rows: y = x / max(float32(sqrt(sum64 x^2)), eps) in fp32."""
+    x32 = np.asarray(x).astype(np.float32)
+    norm = np.sqrt(_sqnorm_f64_lane_order(x32)).astype(np.float32)
+    denom = np.maximum(norm, np.float32(eps)).astype(np.float32)
+    return (x32 / denom[:, None]).astype(np.float32)
+
+
+def row_sqnorms_ref(x: np.ndarray) -> np.ndarray:
+    return _sqnorm_f64_lane_order(np.asarray(x).astype(np.float32)).astype(np.float32)
+
+
+def l2_augment(data_rows: np.ndarray, queries: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """x' = [x, ||x||^2], q' = [2q, -1] (fp32): argmax q'.x' = argmin ||x - q||, the search of
+    notebooks/2.0-Figures-nearest-neighbors.ipynb:54.  Returns (queries' (B,D+1), bank' (D+1,N))."""
+    d32 = np.asarray(data_rows).astype(np.float32)
+    q32 = np.asarray(queries).astype(np.float32)
+    bank = np.concatenate([d32, row_sqnorms_ref(d32)[:, None]], axis=1)
+    qa = np.concatenate([q32 * np.float32(2.0), np.full((q32.shape[0], 1), -1.0, np.float32)], axis=1)
+    return qa, np.ascontiguousarray(bank.T)
+
+
+def l2_topk_o64(data_rows: np.ndarray, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """fp64 L2 distances, ties by lowest row index: what the notebooks' argsort means."""
+    d = np.asarray(data_rows, dtype=np.float64)
+    q = np.asarray(queries, dtype=np.float64)
+    dist = np.sqrt(np.maximum(((q * q).sum(1)[:, None] - 2.0 * q @ d.T + (d * d).sum(1)[None, :]), 0.0))
+    idx = np.argsort(dist, axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(dist, idx, axis=1), idx
+
+
+def metrics_ref(pred: np.ndarray, target: np.ndarray, num_classes: int) -> Dict[str, np.ndarray]:
+    """Confusion counts, macro accuracy / F1 and the row-normalised matrix of
+    src/ssl_wafermap/models/knn.py:104-129 (torchmetrics semantics restated, see b200knn/metrics.py)."""
+    C = int(num_classes)
+    counts = np.zeros((C, C), dtype=np.int64)
+    np.add.at(counts, (np.asarray(target), np.asarray(pred)), 1)
+    c = counts.astype(np.float64)
+    tp, support, predicted = np.diag(c), c.sum(1), c.sum(0)
+    present = (support + predicted) > 0
+    recall = np.divide(tp, support, out=np.zeros(C), where=support > 0)
+    f1 = np.divide(2 * tp, support + predicted, out=np.zeros(C), where=(support + predicted) > 0)
+    n = max(1, int(present.sum()))
+    conf = np.divide(c, support[:, None], out=np.zeros_like(c), where=support[:, None] > 0)
+    return {"counts": counts, "accuracy": float((recall * present).sum() / n),
+            "f1": float((f1 * present).sum() / n), "confusion": conf}

@@ -139,7 +139,10 @@ class PreparedRows:
             return self.hi, self.lo
         if self._f32 is None:
             src, cols = self._src
-            self._f32 = prepare_rows(src, "f32rows", cols).hi
+            # a FeatureBank already holds its rows as zero-padded (N, D_pad) fp32: no second copy
+            own = _padded_rows.get((src.data_ptr(), tuple(src.shape), tuple(src.stride())))
+            own = own() if own is not None else None
+            self._f32 = own if own is not None else prepare_rows(src, "f32rows", cols).hi
         return self._f32, None
 
     def max_norm(self) -> torch.Tensor:
@@ -151,6 +154,52 @@ class PreparedRows:
                                                             out.data_ptr(), _stream()), "row_norm_max")
             self._max_norm = out
         return self._max_norm
+
+
+# (D,N) bank views backed by zero-padded (N, D_pad) fp32 rows (b200knn.bank.FeatureBank)
+_padded_rows = {}
+
+
+def register_padded_rows(bank_view: torch.Tensor, rows_padded: torch.Tensor) -> None:
+    if len(_padded_rows) > 64:
+        for key in [k for k, ref in _padded_rows.items() if ref() is None]:
+            _padded_rows.pop(key)
+    _padded_rows[(bank_view.data_ptr(), tuple(bank_view.shape), tuple(bank_view.stride()))] = weakref.ref(rows_padded)
+
+
+def normalize_rows(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """``F.normalize(x, dim=1)`` of (n, D) rows (reference ``knn.py:77`` / ``:90``) into zero-padded
+    fp32 rows; returns the (n, D) view of the (n, D_pad) result.  fp64 norm in a fixed order."""
+    _require_cuda("x", x)
+    if x.dim() != 2:
+        raise RuntimeError("normalize_rows expects (n, D) row vectors")
+    if x.dtype not in _DTYPES:
+        x = x.float()
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, dim = x.shape
+    out = torch.empty((n, padded_dim(dim)), dtype=torch.float32, device=x.device)
+    if n:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b200knn_normalize_rows(x.data_ptr(), _DTYPES[x.dtype], n, dim, x.stride(0),
+                                                          float(eps), out.data_ptr(), _stream()), "normalize_rows")
+    return out[:, :dim]
+
+
+def row_sqnorms(x: torch.Tensor) -> torch.Tensor:
+    """(n,) fp32 squared L2 norms of (n, D) rows, fp64 accumulation in a fixed order."""
+    _require_cuda("x", x)
+    if x.dtype not in _DTYPES:
+        x = x.float()
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, dim = x.shape
+    out = torch.empty((n,), dtype=torch.float32, device=x.device)
+    if n:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b200knn_row_sqnorms(x.data_ptr(), _DTYPES[x.dtype], n, dim, x.stride(0),
+                                                       out.data_ptr(), _stream()), "row_sqnorms")
+    return out
 
 
 def _layout_of(x: torch.Tensor, vectors_are_columns: bool) -> Tuple[torch.Tensor, int, int]:

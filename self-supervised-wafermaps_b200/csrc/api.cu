@@ -334,6 +334,31 @@ int b200knn_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k, 
                          stream);
 }
 
+int b200knn_normalize_rows(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld, float eps,
+                           float* dst_rows, void* stream) {
+  if (!src || !dst_rows || n_vec < 0 || dim <= 0 || ld < dim) return fail(B200KNN_E_ARG, "normalize_rows: bad argument");
+  if (src_dtype < B200KNN_F32 || src_dtype > B200KNN_BF16) return fail(B200KNN_E_ARG, "normalize_rows: unknown dtype");
+  cudaError_t e = b200knn::launch_normalize_rows(src, src_dtype, n_vec, dim, ld, eps, dst_rows,
+                                                 static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("normalize_rows", e);
+}
+
+int b200knn_row_sqnorms(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld, float* out,
+                        void* stream) {
+  if (!src || !out || n_vec < 0 || dim <= 0 || ld < dim) return fail(B200KNN_E_ARG, "row_sqnorms: bad argument");
+  if (src_dtype < B200KNN_F32 || src_dtype > B200KNN_BF16) return fail(B200KNN_E_ARG, "row_sqnorms: unknown dtype");
+  cudaError_t e = b200knn::launch_row_sqnorm(src, src_dtype, n_vec, dim, ld, out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("row_sqnorms", e);
+}
+
+int b200knn_confusion(const int64_t* pred, const int64_t* target, int64_t n, int C, int64_t* counts,
+                      int32_t* err_flag, void* stream) {
+  if (!pred || !target || !counts || !err_flag || n < 0 || C <= 0) return fail(B200KNN_E_ARG, "confusion: bad argument");
+  if (C > 64) return fail(B200KNN_E_UNSUPPORTED, "confusion: at most 64 classes");
+  cudaError_t e = b200knn::launch_confusion(pred, target, n, C, counts, err_flag, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("confusion", e);
+}
+
 int b200knn_key_sim_column(const uint64_t* keys, int64_t B, int k, int j, float* out, void* stream) {
   if (!keys || !out || B < 0 || k <= 0 || j < 0 || j >= k) return fail(B200KNN_E_ARG, "key_sim_column: bad argument");
   cudaError_t e = b200knn::launch_key_sim_column(keys, B, k, j, out, static_cast<cudaStream_t>(stream));

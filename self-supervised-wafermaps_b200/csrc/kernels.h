@@ -39,6 +39,15 @@ cudaError_t launch_key_sim_column(const uint64_t* keys, int64_t B, int k, int j,
 cudaError_t launch_prepare(const void* src, int src_dtype, int src_layout, int64_t n_vec, int dim,
                            int64_t ld, int mode, void* dst_hi, void* dst_lo, cudaStream_t stream);
 
+// fused F.normalize(dim=1) + relayout into (n_vec, dim_pad) fp32 rows (prepare.cu)
+cudaError_t launch_normalize_rows(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld,
+                                  float eps, float* dst, cudaStream_t stream);
+cudaError_t launch_row_sqnorm(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld, float* out,
+                              cudaStream_t stream);
+// confusion-matrix counts (vote.cu): counts (C,C) int64 += histogram of (target, pred)
+cudaError_t launch_confusion(const int64_t* pred, const int64_t* target, int64_t n, int C, int64_t* counts,
+                             int32_t* err_flag, cudaStream_t stream);
+
 // exact re-scoring of tensor-core candidates (rescore.cu)
 struct RescoreParams {
   const void* q;        // caller queries (B, dim), row-major, ld = q_ld

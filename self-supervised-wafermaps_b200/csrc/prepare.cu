@@ -82,7 +82,65 @@ __global__ void __launch_bounds__(256)
   emit(mode, x, hi, lo, i);
 }
 
+// F.normalize(x, dim=1) of row vectors (reference: src/ssl_wafermap/models/knn.py:77 for bank
+// rows, :90 for queries) fused with the relayout into padded fp32 rows: one warp per row.
+// Defined order, reproducible on the CPU (oracle.normalize_rows_ref): lane l adds the squares
+// of columns l, l+32, ... in fp64 (each square is exact), the 32 partials are combined by an
+// xor butterfly (16, 8, 4, 2, 1), norm = float(sqrt(total)), y = x / max(norm, eps) in fp32.
+__global__ void __launch_bounds__(256)
+    normalize_rows_kernel(const void* __restrict__ src, int dtype, int64_t n_vec, int dim, int dim_pad,
+                          int64_t ld, float eps, float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_vec) return;
+  double acc = 0.0;
+  for (int d = lane; d < dim; d += 32) {
+    const double v = double(ld_f32(src, dtype, row * ld + d));
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const float denom = fmaxf(float(sqrt(acc)), eps);
+  for (int d = lane; d < dim_pad; d += 32)
+    dst[row * dim_pad + d] = d < dim ? __fdiv_rn(ld_f32(src, dtype, row * ld + d), denom) : 0.0f;
+}
+
+// ||row||^2 in the same defined order as normalize_rows_kernel, rounded once to fp32
+__global__ void __launch_bounds__(256)
+    row_sqnorm_kernel(const void* __restrict__ src, int dtype, int64_t n_vec, int dim, int64_t ld,
+                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_vec) return;
+  double acc = 0.0;
+  for (int d = lane; d < dim; d += 32) {
+    const double v = double(ld_f32(src, dtype, row * ld + d));
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = float(acc);
+}
+
 }  // namespace
+
+cudaError_t launch_row_sqnorm(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld, float* out,
+                              cudaStream_t stream) {
+  if (n_vec == 0) return cudaSuccess;
+  const int64_t blocks = (n_vec * 32 + 255) / 256;
+  row_sqnorm_kernel<<<unsigned(blocks), 256, 0, stream>>>(src, src_dtype, n_vec, dim, ld, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_normalize_rows(const void* src, int src_dtype, int64_t n_vec, int dim, int64_t ld,
+                                  float eps, float* dst, cudaStream_t stream) {
+  if (n_vec == 0) return cudaSuccess;
+  const int dim_pad = (dim + 63) / 64 * 64;
+  const int64_t blocks = (n_vec * 32 + 255) / 256;
+  normalize_rows_kernel<<<unsigned(blocks), 256, 0, stream>>>(src, src_dtype, n_vec, dim, dim_pad, ld, eps,
+                                                              dst);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_prepare(const void* src, int src_dtype, int src_layout, int64_t n_vec, int dim,
                            int64_t ld, int mode, void* dst_hi, void* dst_lo, cudaStream_t stream) {

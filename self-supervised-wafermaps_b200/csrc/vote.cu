@@ -84,7 +84,38 @@ __global__ void __launch_bounds__(kVoteWarps * 32)
   }
 }
 
+// counts[t * C + p] += 1 for every (target t, prediction p): the confusion matrix the
+// reference builds with torchmetrics after each validation epoch
+// (src/ssl_wafermap/models/knn.py:104-129).  Block-private histograms in shared memory
+// (C <= 64), one global atomic per non-zero cell per block.
+__global__ void __launch_bounds__(256)
+    confusion_kernel(const int64_t* __restrict__ pred, const int64_t* __restrict__ target, int64_t n, int C,
+                     unsigned long long* __restrict__ counts, int32_t* __restrict__ err_flag) {
+  extern __shared__ unsigned int cm_smem[];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) cm_smem[i] = 0u;
+  __syncthreads();
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t p = pred[i], t = target[i];
+    if (p >= 0 && p < C && t >= 0 && t < C) atomicAdd(&cm_smem[t * C + p], 1u);
+    else atomicExch(err_flag, 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (cm_smem[i]) atomicAdd(&counts[i], static_cast<unsigned long long>(cm_smem[i]));
+}
+
 }  // namespace
+
+cudaError_t launch_confusion(const int64_t* pred, const int64_t* target, int64_t n, int C, int64_t* counts,
+                             int32_t* err_flag, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  if (C > 64) return cudaErrorInvalidValue;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  confusion_kernel<<<unsigned(blocks), 256, size_t(C) * C * sizeof(unsigned int), stream>>>(
+      pred, target, n, C, reinterpret_cast<unsigned long long*>(counts), err_flag);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_vote(const uint64_t* keys, const int64_t* labels, int64_t B, int k,
                         int64_t n_labels, int64_t label_offset, int C, double t, int64_t* pred,
