@@ -32,6 +32,7 @@ from . import _lib
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
 TC_MODES = ("bf16", "tf32x3", "bf16x3")  # raw tensor-core similarity modes
+MAX_K = 992  # largest k of the streaming candidate lists (capacity 1024, include/b200knn.h)
 MAX_BF16_DIM = 768  # widest (padded) vector whose query tile the BF16 kernel can keep resident
 
 _default_mode = os.environ.get("B200KNN_MODE", "fp32")
@@ -589,9 +590,9 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
     cfg = LEVELS[level]
     B, D = feature.shape
     N = feature_bank.shape[1]
-    k_in = min(N, k + cfg["margin"])
-    if lib.b200knn_topk_workspace_bytes(max(B, 1), N, D, k_in, _lib.MODES[cfg["cand"]]) == 0:
-        k_in = min(N, k + 8)  # k too large for the wide margin's list capacity
+    # the streaming lists hold at most MAX_K keys: near that limit the margin shrinks (and with it
+    # the chance to certify; uncertified rows still end up exact through the next level)
+    k_in = min(N, k + cfg["margin"], max(k, MAX_K))
     dev = feature.device
     # no repair pass on the candidates: a row its sampled threshold starved has an empty k_in-th
     # slot, which the re-scoring kernel reports as uncertified

@@ -275,3 +275,69 @@ def test_other_vector_dims(D, mode):
         assert recall >= 0.95 and err <= 1e-2
     else:
         assert recall >= 0.995 and err <= 6e-5
+
+
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "fp32"])
+def test_tie_flood_and_degenerate_banks(mode):
+    """All similarities equal (identical bank rows, or a zero query): the radix-select prune cannot
+    separate anything and must hand over to the exact sort; order is then by lowest index."""
+    D, N, k = 512, 70000, 200
+    g = torch.Generator(device=DEV).manual_seed(3)
+    row = torch.nn.functional.normalize(torch.randn(1, D, generator=g, device=DEV), dim=1)
+    bank = row.repeat(N, 1).t().contiguous()                      # N identical rows
+    q = torch.nn.functional.normalize(torch.randn(130, D, generator=g, device=DEV), dim=1)
+    q[5] = 0                                                      # zero query: every sim is +0
+    q[6] = -q[7]
+    sims, idx = b200knn.knn_topk(q, bank, k, mode=mode)
+    want = torch.arange(k, device=DEV).expand(130, k)
+    assert torch.equal(idx, want)
+    assert bool((sims[5] == 0).all())
+    assert bool((sims == sims[:, :1]).all())
+    # a bank whose first half duplicates its second half: every neighbour appears twice, low index first
+    half = torch.nn.functional.normalize(torch.randn(4000, D, generator=g, device=DEV), dim=1)
+    bank2 = torch.cat([half, half], 0).t().contiguous()
+    s2, i2 = b200knn.knn_topk(q[8:72].contiguous(), bank2, 20, mode=mode)  # (not the zero query)
+    assert torch.equal(i2[:, 0::2] + 4000, i2[:, 1::2])
+    assert torch.equal(s2[:, 0::2], s2[:, 1::2])
+
+
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "fp32", "exact"])
+@pytest.mark.parametrize("B,N,k", [(1, 200, 200), (3, 257, 1), (129, 300, 300), (64, 1500, 992), (2, 17, 5)])
+def test_small_and_extreme_shapes(mode, B, N, k):
+    """k = N (every row is a neighbour), one query, banks smaller than one tile, the largest k."""
+    D = 128
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + N)
+    bank = torch.randn(N, D, generator=g, device=DEV).t().contiguous()
+    q = torch.randn(B, D, generator=g, device=DEV)
+    ek = b200knn.topk_keys(q, bank, k, mode="exact")
+    ss, si = O.topk_seqfma(q.cpu().numpy(), bank.cpu().numpy(), k)
+    es, ei = b200knn.decode_keys(ek)
+    assert np.array_equal(ei.cpu().numpy(), si) and np.array_equal(es.cpu().numpy().view(np.uint32), ss.view(np.uint32))
+    tk = b200knn.topk_keys(q, bank, k, mode=mode)
+    if mode in ("fp32", "exact"):
+        assert torch.equal(tk, ek)
+    else:
+        ts, ti = b200knn.decode_keys(tk)
+        assert bool((ti >= 0).all()) and bool((ti < N).all())
+        if k == N:  # every row must appear exactly once
+            assert torch.equal(torch.sort(ti, dim=1).values, torch.arange(N, device=DEV).expand(B, N))
+        tol = {"bf16": 0.3, "bf16x3": 2e-3, "tf32x3": 5e-4}[mode]
+        assert float((ts[:, 0] - es[:, 0]).abs().max()) <= tol
+
+
+def test_k_limits_and_empty_batch():
+    D, N = 64, 2000
+    bank = torch.randn(N, D, device=DEV).t().contiguous()
+    q = torch.randn(4, D, device=DEV)
+    for mode in ("exact", "bf16", "fp32"):
+        with pytest.raises(RuntimeError):
+            b200knn.topk_keys(q, bank, 993, mode=mode)          # list capacity: k <= 992
+        with pytest.raises(RuntimeError, match="out of range"):
+            b200knn.topk_keys(q, bank, N + 1, mode=mode)
+        empty = b200knn.topk_keys(q[:0], bank, 10, mode=mode)
+        assert empty.shape == (0, 10)
+        b200knn.set_default_mode(mode)
+        try:
+            assert b200knn.knn_predict(q[:0], bank, torch.zeros(N, dtype=torch.int64, device=DEV), 3, 10).shape == (0, 3)
+        finally:
+            b200knn.set_default_mode("exact")
