@@ -29,6 +29,7 @@ for _p in (ROOT, os.path.join(ROOT, "self-supervised-wafermaps_b200"), os.path.j
         sys.path.insert(0, _p)
 
 N_BANK, DIM, KNN_K, KNN_T, N_CLASSES = 811457, 512, 200, 0.1, 9
+METRIC = "kNN queries/s @811k×512 bank, k=200"
 WAVE = 148 * 128  # queries one resident wave of CTAs covers
 
 
@@ -53,28 +54,34 @@ def ncu_traffic(mode, Q, N, world):
     return None
 
 
-def make_inputs(device, n_bank, n_query, dim, seed):
+def make_inputs(device, n_bank, n_query, dim, seed, row_range=None):
     """clustered synthetic embeddings generated on the device under test, in chunks of 65,536
-    rows so results do not depend on the total size."""
+    rows with one generator per chunk, so a rank can generate only the bank rows it owns
+    (row_range) and results do not depend on the total size.  Labels are
+    generated for all rows (they are replicated)."""
     import torch
 
-    g = torch.Generator(device=device).manual_seed(seed)
+    g0 = torch.Generator(device=device).manual_seed(seed)
     prior = torch.tensor([859, 111, 1037, 1936, 719, 30, 173, 239, 7345], dtype=torch.float64, device=device)
-    cent = torch.nn.functional.normalize(torch.randn(N_CLASSES, dim, generator=g, device=device), dim=1)
+    cent = torch.nn.functional.normalize(torch.randn(N_CLASSES, dim, generator=g0, device=device), dim=1)
+    lo_own, hi_own = row_range if row_range is not None else (0, n_bank)
 
-    def rows(n):
-        out = torch.empty(n, dim, device=device)
+    def rows(n, stream_id, lo_want, hi_want):
+        out = torch.empty(max(0, hi_want - lo_want), dim, device=device)
         lab = torch.empty(n, dtype=torch.int64, device=device)
-        for lo in range(0, n, 65536):
+        for ci, lo in enumerate(range(0, n, 65536)):
             hi = min(n, lo + 65536)
+            g = torch.Generator(device=device).manual_seed(seed * 1000003 + stream_id * 100003 + ci)
             l = torch.multinomial(prior, hi - lo, replacement=True, generator=g)
-            x = cent[l] + 1.4 * torch.randn(hi - lo, dim, generator=g, device=device) / dim ** 0.5
-            out[lo:hi] = torch.nn.functional.normalize(x, dim=1)
             lab[lo:hi] = l
+            a, b = max(lo, lo_want), min(hi, hi_want)
+            if a < b:
+                x = cent[l] + 1.4 * torch.randn(hi - lo, dim, generator=g, device=device) / dim ** 0.5
+                out[a - lo_want:b - lo_want] = torch.nn.functional.normalize(x, dim=1)[a - lo:b - lo]
         return out, lab
 
-    bank_nd, labels = rows(n_bank)
-    q, _ = rows(n_query)
+    bank_nd, labels = rows(n_bank, 1, lo_own, hi_own)
+    q, _ = rows(n_query, 2, 0, n_query)
     return bank_nd, labels, q
 
 
@@ -168,7 +175,7 @@ def run_reference(args):
     rate = batch * len(times) / sum(times)
     sample = f"{len(times)} calls of B={batch} queries against the full {N_BANK}x{DIM} bank, k={KNN_K}"
     line = {
-        "impl": "reference", "metric": "kNN queries/s @811k×512 bank, k=200", "value": rate, "unit": "queries/s",
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -183,6 +190,7 @@ def run_reference(args):
 
 
 def main():
+    global DIM, KNN_K, N_BANK
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -192,7 +200,10 @@ def main():
     ap.add_argument("--queries", type=int, default=4 * WAVE, help="queries per step (default 75,776 = 4 waves)")
     ap.add_argument("--bank", type=int, default=N_BANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dim", type=int, default=DIM, help="vector dimension (default 512; 768 = config c5)")
+    ap.add_argument("--k", type=int, default=KNN_K)
     args = ap.parse_args()
+    DIM, KNN_K, N_BANK = args.dim, args.k, args.bank
     if args.impl == "reference":
         return run_reference(args)
 
@@ -213,10 +224,10 @@ def main():
     Q, N, mode = args.queries, args.bank, args.mode
     b200knn.set_default_mode(mode)
 
-    bank_nd, labels, q = make_inputs(dev, N, Q, DIM, seed=811)
+    lo, hi = b200knn.shard_bounds(N, world, rank)
+    bank_nd, labels, q = make_inputs(dev, N, Q, DIM, seed=811, row_range=(lo, hi) if world > 1 else None)
     if world > 1:
-        lo, hi = b200knn.shard_bounds(N, world, rank)
-        shard = bank_nd[lo:hi].t().contiguous()  # this rank's (D, rows) slice, reference layout
+        shard = bank_nd.t().contiguous()  # this rank's (D, rows) slice, reference layout
         del bank_nd
         sb = b200knn.ShardedBank(shard, labels, N, mode=mode)
         bank = shard
@@ -384,7 +395,8 @@ def main():
         gpu_launches = n_abi_kernels + splits_extra
         roof["traffic"] = ncu_traffic(mode, Q, N, world)
         line = {
-            "metric": "kNN queries/s @811k×512 bank, k=200", "value": value, "unit": "queries/s",
+            "metric": METRIC if (N, DIM, KNN_K) == (811457, 512, 200) else f"kNN queries/s @{N}x{DIM} bank, k={KNN_K}",
+            "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "exact": "f32", "fp32": "bf16x3+f32",
