@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200KNN_VERSION 100 /* 0.1.0 */
+#define B200KNN_VERSION 110 /* 0.1.1: b200knn_rescore takes a workspace and the two extra certificate terms */
 
 /* error codes */
 #define B200KNN_OK 0
@@ -217,12 +217,17 @@ int b200knn_key_sim_column(const uint64_t* keys, int64_t B, int k, int j, float*
  *   out_keys : (B, k_out) keys with EXACT sims = fmaf chain over d (MODE_EXACT's
  *              definition), canonical order
  *   uncertified[b] = 1 when  exact_sim(rank k_out) <= approx_sim(rank k_in) + E,
- *              E = err_coef * ||q_b|| * (*bank_max_norm)  — the candidate set is
- *              then not proven to contain the true top-k and the caller must
- *              recompute row b in MODE_EXACT; *n_uncertified counts such rows
- *              (caller zeroes it).  A row whose k_in-th candidate slot is empty
- *              although k_in < N (a b200knn_topk_ex threshold starved it) is
- *              uncertified as well.
+ *              E = err_coef * ||q_b|| * M + err_abs * (||q_b|| + M),  M = *bank_max_norm
+ *              — the candidate set is then not proven to contain the true top-k and the
+ *              caller must recompute row b in MODE_EXACT; *n_uncertified counts such rows
+ *              (caller zeroes it).  max_abs > 0 additionally refuses rows with ||q_b|| or M
+ *              >= max_abs (operand range of a half-precision candidate pass).  A row whose
+ *              k_in-th candidate slot is empty although k_in < N (a b200knn_topk_ex
+ *              threshold starved it) is uncertified as well.
+ *   workspace: optional, b200knn_rescore_workspace_bytes(B, k_in) bytes of device memory.
+ *              With it (and fp32 queries, rows_b NULL) the rows are gathered by a persistent
+ *              TMA-pipelined kernel (cp.async.bulk per candidate row) and ranked by a second
+ *              one; without it a single block-per-query kernel does both.  Same results.
  * b200knn_row_norm_max writes max_n ||row_n|| (x1.001) to *out_dev.
  */
 int b200knn_row_norm_max(const float* rows_a, const float* rows_b, int64_t n,
@@ -230,9 +235,11 @@ int b200knn_row_norm_max(const float* rows_a, const float* rows_b, int64_t n,
 int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_a,
                     const float* rows_b, int64_t N, int dim,
                     const uint64_t* cand_keys, int64_t B, int k_in, int k_out,
-                    int64_t idx_offset, float err_coef, const float* bank_max_norm,
-                    uint64_t* out_keys, int32_t* uncertified,
-                    int32_t* n_uncertified, void* stream);
+                    int64_t idx_offset, float err_coef, float err_abs, float max_abs,
+                    const float* bank_max_norm, uint64_t* out_keys, int32_t* uncertified,
+                    int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
+                    void* stream);
+size_t b200knn_rescore_workspace_bytes(int64_t B, int k_in);
 
 /*
  * SURVEY.md §8(f) rows — the steps either side of knn_predict in the reference.

@@ -21,6 +21,7 @@ allocator, and calls through the C ABI on the current CUDA stream.
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 import weakref
 from typing import Optional, Tuple
@@ -600,17 +601,21 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
     pb = bank_cache.get(feature_bank, cfg["cand"])
     rows_a, rows_b = pb.rescore_rows()
     max_norm = pb.max_norm()
-    q = feature if feature.dtype in _DTYPES else feature.float()
+    # fp32 queries select the TMA-pipelined re-scoring kernels (fp16/bf16 -> fp32 is exact)
+    q = feature if feature.dtype == torch.float32 else feature.float()
     if q.stride(1) != 1:
         q = q.contiguous()
     out = torch.empty((B, k), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         flags = torch.empty((B,), dtype=torch.int32, device=dev)
         n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.b200knn_rescore_workspace_bytes(B, k_in)) if rows_b is None else 0
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
         _lib.check(lib.b200knn_rescore(q.data_ptr(), _DTYPES[q.dtype], q.stride(0), rows_a.data_ptr(),
                                        _ptr(rows_b), N, D, cand.data_ptr(), B, k_in, k, idx_offset,
-                                       float(cfg["err_coef"]), max_norm.data_ptr(), out.data_ptr(),
-                                       flags.data_ptr(), n_bad.data_ptr(), _stream()), "rescore")
+                                       float(cfg["err_coef"]), float(cfg.get("err_abs", 0.0)) * math.sqrt(padded_dim(D)),
+                                       float(cfg.get("max_abs", 0.0)), max_norm.data_ptr(), out.data_ptr(),
+                                       flags.data_ptr(), n_bad.data_ptr(), _ptr(ws), ws_bytes, _stream()), "rescore")
     return out, flags, n_bad
 
 

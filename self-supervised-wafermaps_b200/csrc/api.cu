@@ -277,8 +277,9 @@ int b200knn_row_norm_max(const float* rows_a, const float* rows_b, int64_t n, in
 
 int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_a, const float* rows_b,
                     int64_t N, int dim, const uint64_t* cand_keys, int64_t B, int k_in, int k_out,
-                    int64_t idx_offset, float err_coef, const float* bank_max_norm,
-                    uint64_t* out_keys, int32_t* uncertified, int32_t* n_uncertified, void* stream) {
+                    int64_t idx_offset, float err_coef, float err_abs, float max_abs,
+                    const float* bank_max_norm, uint64_t* out_keys, int32_t* uncertified,
+                    int32_t* n_uncertified, void* workspace, size_t workspace_bytes, void* stream) {
   if (!q || !rows_a || !cand_keys || !bank_max_norm || !out_keys || !uncertified || !n_uncertified)
     return fail(B200KNN_E_ARG, "rescore: null pointer");
   if (B < 0 || N <= 0 || dim <= 0 || k_out <= 0 || k_in < k_out || k_in > 1024)
@@ -299,12 +300,19 @@ int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_
   p.all_rows = (int64_t(k_in) >= N) ? 1 : 0;
   p.idx_offset = idx_offset;
   p.err_coef = err_coef;
+  p.err_abs = err_abs;
+  p.max_abs = max_abs;
   p.bank_max_norm = bank_max_norm;
   p.out = out_keys;
   p.uncertified = uncertified;
   p.n_uncertified = n_uncertified;
-  cudaError_t e = b200knn::launch_rescore(p, static_cast<cudaStream_t>(stream));
+  cudaError_t e = b200knn::launch_rescore(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? B200KNN_OK : fail_cuda("rescore", e);
+}
+
+size_t b200knn_rescore_workspace_bytes(int64_t B, int k_in) {
+  if (B <= 0 || k_in <= 0) return 0;
+  return b200knn::rescore_workspace_bytes(B, k_in);
 }
 
 int b200knn_decode_keys(const uint64_t* keys, int64_t n_keys, float* sims, int64_t* idx, void* stream) {

@@ -61,13 +61,18 @@ struct RescoreParams {
   int k_in, k_out;
   int all_rows;  // k_in >= N: every bank row is a candidate, empty slots are legitimate
   int64_t idx_offset;
-  float err_coef;
+  float err_coef;              // E = err_coef * ||q|| * M + err_abs * (||q|| + M),  M = *bank_max_norm
+  float err_abs;
+  float max_abs;               // > 0: rows with ||q|| or M >= max_abs are uncertified (operand range)
   const float* bank_max_norm;  // device scalar
   uint64_t* out;               // (B, k_out)
   int32_t* uncertified;        // (B,)
   int32_t* n_uncertified;      // device counter (caller zeroes)
 };
-cudaError_t launch_rescore(const RescoreParams& p, cudaStream_t stream);
+// workspace (optional, rescore_workspace_bytes): selects the TMA-pipelined two-kernel variant
+cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream);
+size_t rescore_workspace_bytes(int64_t B, int k_in);
 cudaError_t launch_row_norm_max(const float* a, const float* b, int64_t n, int dim_pad, float* out,
                                 cudaStream_t stream);
 

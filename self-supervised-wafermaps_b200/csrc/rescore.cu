@@ -17,15 +17,44 @@
 //
 // HBM/L2-bound gather: per query k_in rows of D fp32 (k_in*D*4 B, x2 in TF32X3
 // where x = hi + lo is reassembled), 8*k B out.
+//
+// Two implementations of the same arithmetic:
+//  * rescore_dot_kernel + rescore_select_kernel (fp32 queries, one fp32 row array, caller
+//    workspace): persistent warps, each owning a ring of shared-memory stages that the
+//    TMA engine fills with 32 candidate rows x CHUNK columns (one cp.async.bulk per row, the
+//    query chunk by cp.async, all completing on the stage's mbarrier).  Lane c then walks
+//    row c with conflict-free LDS.128 (row pitch CHUNK+4 floats) — the fma chain of one
+//    candidate is sequential by definition, so the parallelism is 32 candidates per warp
+//    and the copies of the next stage are in flight while the chain runs.  The exact keys go
+//    to the workspace; a second kernel sorts them per query and evaluates the certificate.
+//  * rescore_kernel (any query dtype, optional lo array, no workspace): one block per
+//    query, rows staged by plain loads.  Kept for the TF32X3 operands and small calls.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "../../include/b200knn.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace b200knn {
 namespace {
+
+// Certificate of one row (see the header): kth = exact key at rank k_out, last = approximate key
+// at rank k_in, qn = ||q|| (inflated by the caller for its rounding).
+__device__ __forceinline__ int certified(const RescoreParams& p, uint64_t kth, uint64_t last, float qn) {
+  if (last == 0) {
+    // an empty slot certifies the row only when every bank row was a candidate (k_in >= N);
+    // otherwise the candidate pass ran under an admission threshold that starved this row
+    return p.all_rows ? 1 : 0;
+  }
+  const float m = *p.bank_max_norm;
+  if (p.max_abs > 0.0f && !(qn < p.max_abs && m < p.max_abs)) return 0;  // operand range of the candidate pass
+  const float e = p.err_coef * qn * m + p.err_abs * (qn + m);
+  return (kth != 0) && (key_sim(kth) > key_sim(last) + e);
+}
 
 constexpr int kWarps = 4;
 constexpr int kChunk = 64;            // d-columns staged per step
@@ -108,19 +137,216 @@ __global__ void __launch_bounds__(kWarps * 32)
     kth = __shfl_sync(kFull, kth, (p.k_out - 1) & 31);
     if (lane == 0) {
       const uint64_t last = cand[p.k_in - 1];  // worst candidate under the approximate order
-      int ok = 1;
-      if (last == 0) {
-        // an empty slot certifies the row only when every bank row was a candidate (k_in >= N);
-        // otherwise the candidate pass ran under an admission threshold that starved this row
-        ok = p.all_rows ? 1 : 0;
-      } else {
-        const float qn = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.001f;
-        const float e = p.err_coef * qn * (*p.bank_max_norm);
-        ok = (kth != 0) && (key_sim(kth) > key_sim(last) + e);
-      }
+      const float qn = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.001f;
+      const int ok = certified(p, kth, last, qn);
       p.uncertified[b] = ok ? 0 : 1;
       if (!ok) atomicAdd(p.n_uncertified, 1);
     }
+  }
+}
+
+
+// ------------------------------------------------------------------ pipelined variant
+// One work unit = 32 consecutive candidate slots of one query; a step = one unit x one
+// CHUNK of columns.  Each warp owns STAGES stages and a contiguous range of units.
+template <int CHUNK>
+struct DotStage {
+  static constexpr int kPitch = CHUNK + 4;  // floats; lane c reads float4 j of row c: bank group (c + j) mod 8
+  float rows[32 * kPitch];
+  float q[CHUNK];
+  uint32_t klo[32];  // low key word (0xFFFFFFFF - idx) of each lane's candidate, 0 = empty slot
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int CHUNK, int STAGES>
+__global__ void __launch_bounds__(256)
+    rescore_dot_kernel(RescoreParams p, uint64_t* __restrict__ tmp, int n_groups, int64_t n_units,
+                       int q_vec16) {
+  using Stage = DotStage<CHUNK>;
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  const int n_warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Stage* stages = reinterpret_cast<Stage*>(rs_smem) + size_t(warp) * STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + sizeof(Stage) * size_t(n_warps) * STAGES) +
+                   warp * STAGES;
+  if (lane == 0) {
+    // per phase: lane 0's arrive.expect_tx + one cp.async "noinc" arrival per lane (query chunk)
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(ptx::smem_u32(&bars[s]), 33);
+    ptx::fence_barrier_init();
+  }
+  __syncwarp();
+
+  const int64_t wg = int64_t(blockIdx.x) * n_warps + warp, tw = int64_t(gridDim.x) * n_warps;
+  const int64_t u_begin = n_units * wg / tw, u_end = n_units * (wg + 1) / tw;
+  if (u_begin >= u_end) return;
+  const int n_chunks = (p.dim_pad + CHUNK - 1) / CHUNK;
+  const float* q32 = static_cast<const float*>(p.q);
+
+  auto load_key = [&](int64_t b, int g) -> uint64_t {
+    const int c = g * 32 + lane;
+    return (b < p.B && c < p.k_in) ? p.cand[b * p.k_in + c] : 0ull;
+  };
+
+  // producer cursor: unit (pb, pg), chunk pc; this lane's key of that unit and of the next one
+  int64_t pu = u_begin, pb = u_begin / n_groups;
+  int pg = int(u_begin - pb * n_groups), pc = 0, ps = 0;
+  uint64_t p_key = load_key(pb, pg);
+  uint64_t p_key_next = (pu + 1 < u_end) ? (pg + 1 < n_groups ? load_key(pb, pg + 1) : load_key(pb + 1, 0)) : 0ull;
+
+  auto produce = [&]() {
+    Stage& st = stages[ps];
+    const uint32_t bar = ptx::smem_u32(&bars[ps]);
+    const int64_t row = p_key != 0 ? key_idx(p_key) - p.idx_offset : -1;
+    const int d0 = pc * CHUNK;
+    const int len = min(CHUNK, p.dim_pad - d0);
+    const unsigned valid = __ballot_sync(kFull, row >= 0);
+    if (lane == 0) ptx::mbar_expect_tx(bar, uint32_t(__popc(valid)) * uint32_t(len) * 4u);
+    if (row >= 0)
+      bulk_g2s(ptx::smem_u32(st.rows + lane * Stage::kPitch), p.rows_a + row * p.dim_pad + d0,
+               uint32_t(len) * 4u, bar);
+    const float* qrow = q32 + pb * p.q_ld;
+    if (q_vec16) {
+      for (int i = lane; i < len / 4; i += 32) {
+        const int d = d0 + 4 * i;
+        const int nb = max(0, min(16, (p.dim - d) * 4));
+        cp_async16_zfill(ptx::smem_u32(st.q + 4 * i), qrow + (nb > 0 ? d : 0), uint32_t(nb));
+      }
+    } else {
+      for (int i = lane; i < len; i += 32) {
+        const int d = d0 + i;
+        cp_async4_zfill(ptx::smem_u32(st.q + i), qrow + (d < p.dim ? d : 0), d < p.dim ? 4u : 0u);
+      }
+    }
+    cp_async_arrive_noinc(bar);
+    if (pc == 0) st.klo[lane] = uint32_t(p_key);
+    if (++ps == STAGES) ps = 0;
+    if (++pc == n_chunks) {
+      pc = 0;
+      ++pu;
+      if (++pg == n_groups) {
+        pg = 0;
+        ++pb;
+      }
+      p_key = p_key_next;
+      // prefetch the keys of the unit after the one now being produced
+      int64_t nb = pb;
+      int ng = pg + 1;
+      if (ng == n_groups) {
+        ng = 0;
+        ++nb;
+      }
+      p_key_next = (pu + 1 < u_end) ? load_key(nb, ng) : 0ull;
+    }
+  };
+
+  const int64_t n_steps = (u_end - u_begin) * n_chunks;
+  for (int64_t t = 0; t < STAGES && t < n_steps; ++t) produce();
+
+  int cs = 0, cc = 0;
+  uint32_t phase = 0, klo = 0;
+  int64_t cu = u_begin;
+  float acc = 0.0f;
+  for (int64_t t = 0; t < n_steps; ++t) {
+    Stage& st = stages[cs];
+    ptx::mbar_wait(ptx::smem_u32(&bars[cs]), phase, nullptr, 7);
+    if (cc == 0) {
+      acc = 0.0f;
+      klo = st.klo[lane];
+    }
+    const int len4 = min(CHUNK, p.dim_pad - cc * CHUNK) / 4;
+    const float4* xr = reinterpret_cast<const float4*>(st.rows + lane * Stage::kPitch);
+    const float4* qr = reinterpret_cast<const float4*>(st.q);
+    // len4 is a multiple of 16 (dim_pad is a multiple of 64).  The 16 loads of a block are issued
+    // before its fma chain starts, and the next block's loads while the chain runs.
+    float4 x[8], w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] = xr[i];
+      w[i] = qr[i];
+    }
+#pragma unroll 1
+    for (int j = 0; j < len4; j += 8) {
+      float4 xn[8], wn[8];
+      const int jn = (j + 8 < len4) ? j + 8 : j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xn[i] = xr[jn + i];
+        wn[i] = qr[jn + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc = __fmaf_rn(w[i].x, x[i].x, acc);
+        acc = __fmaf_rn(w[i].y, x[i].y, acc);
+        acc = __fmaf_rn(w[i].z, x[i].z, acc);
+        acc = __fmaf_rn(w[i].w, x[i].w, acc);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] = xn[i];
+        w[i] = wn[i];
+      }
+    }
+    if (++cc == n_chunks) {
+      cc = 0;
+      tmp[cu * 32 + lane] = klo != 0 ? ((uint64_t(f32_to_orderable(acc)) << 32) | uint64_t(klo)) : 0ull;
+      ++cu;
+    }
+    // the stage is free: order this warp's generic-proxy reads before the async-proxy refill
+    __syncwarp();
+    ptx::fence_proxy_async();
+    if (t + STAGES < n_steps) produce();
+    if (++cs == STAGES) {
+      cs = 0;
+      phase ^= 1;
+    }
+  }
+}
+
+// exact keys of one query (n_groups*32 slots in the workspace) -> best k_out, sorted; certificate
+template <int ITEMS>
+__global__ void __launch_bounds__(128)
+    rescore_select_kernel(RescoreParams p, const uint64_t* __restrict__ tmp, int n_groups) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = int64_t(blockIdx.x) * 4 + warp;
+  if (b >= p.B) return;
+  const uint64_t* mine = tmp + b * n_groups * 32;
+  uint64_t v[ITEMS];
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) v[r] = r < n_groups ? mine[r * 32 + lane] : 0ull;
+  const float* qrow = static_cast<const float*>(p.q) + b * p.q_ld;
+  float qq = 0.0f;
+  for (int d = lane; d < p.dim; d += 32) qq = fmaf(qrow[d], qrow[d], qq);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(kFull, qq, o);
+  warp_sort_desc<ITEMS>(v, lane);
+  uint64_t kth = 0;
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int i = r * 32 + lane;
+    if (i < p.k_out) p.out[b * p.k_out + i] = v[r];
+    kth = (i == p.k_out - 1) ? v[r] : kth;
+  }
+  kth = __shfl_sync(kFull, kth, (p.k_out - 1) & 31);
+  if (lane == 0) {
+    const uint64_t last = p.cand[b * p.k_in + p.k_in - 1];  // worst candidate under the approximate order
+    const int ok = certified(p, kth, last, sqrtf(qq) * 1.001f);
+    p.uncertified[b] = ok ? 0 : 1;
+    if (!ok) atomicAdd(p.n_uncertified, 1);
   }
 }
 
@@ -156,11 +382,67 @@ cudaError_t launch_rescore_t(const RescoreParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+
+template <int ITEMS>
+cudaError_t launch_select_t(const RescoreParams& p, const uint64_t* tmp, int n_groups, cudaStream_t stream) {
+  rescore_select_kernel<ITEMS><<<unsigned((p.B + 3) / 4), 128, 0, stream>>>(p, tmp, n_groups);
+  return cudaGetLastError();
+}
+
+// experiment switch B200KNN_RESCORE_CHUNK=128|256 (columns per stage; default 128)
+int dot_chunk() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("B200KNN_RESCORE_CHUNK");
+    v = (e != nullptr && atoi(e) == 256) ? 256 : 128;
+  }
+  return v;
+}
+
+template <int CHUNK, int STAGES>
+cudaError_t launch_dot_t(const RescoreParams& p, uint64_t* tmp, int n_groups, cudaStream_t stream) {
+  constexpr int kSmem = 232448 - 1024;
+  const size_t per_warp = STAGES * (sizeof(DotStage<CHUNK>) + sizeof(uint64_t));
+  int warps = int(kSmem / per_warp);
+  if (warps > 8) warps = 8;
+  if (warps < 1) return cudaErrorNotSupported;
+  const int64_t n_units = p.B * n_groups;
+  int64_t blocks = (n_units + warps - 1) / warps;
+  if (blocks > 148) blocks = 148;
+  const size_t smem = per_warp * warps;
+  auto kern = rescore_dot_kernel<CHUNK, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  const uintptr_t qa = reinterpret_cast<uintptr_t>(p.q);
+  const int q_vec16 = (qa % 16 == 0 && p.q_ld % 4 == 0) ? 1 : 0;
+  kern<<<unsigned(blocks), warps * 32, smem, stream>>>(p, tmp, n_groups, n_units, q_vec16);
+  return cudaGetLastError();
+}
 }  // namespace
 
-cudaError_t launch_rescore(const RescoreParams& p, cudaStream_t stream) {
+size_t rescore_workspace_bytes(int64_t B, int k_in) {
+  return size_t(B) * size_t((k_in + 31) / 32) * 32 * sizeof(uint64_t);
+}
+
+cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
   const int items = (p.k_in + 31) / 32;
+  const bool pipelined = workspace != nullptr && workspace_bytes >= rescore_workspace_bytes(p.B, p.k_in) &&
+                         p.rows_b == nullptr && p.q_dtype == B200KNN_F32 &&
+                         reinterpret_cast<uintptr_t>(p.rows_a) % 16 == 0;
+  if (pipelined) {
+    uint64_t* tmp = static_cast<uint64_t*>(workspace);
+    cudaError_t e = dot_chunk() == 256 ? launch_dot_t<256, 2>(p, tmp, items, stream)
+                                       : launch_dot_t<128, 2>(p, tmp, items, stream);
+    if (e != cudaSuccess) return e;
+    if (items <= 2) return launch_select_t<2>(p, tmp, items, stream);
+    if (items <= 4) return launch_select_t<4>(p, tmp, items, stream);
+    if (items <= 8) return launch_select_t<8>(p, tmp, items, stream);
+    if (items <= 16) return launch_select_t<16>(p, tmp, items, stream);
+    if (items <= 32) return launch_select_t<32>(p, tmp, items, stream);
+    return cudaErrorInvalidValue;
+  }
   if (items <= 2) return launch_rescore_t<2>(p, stream);
   if (items <= 4) return launch_rescore_t<4>(p, stream);
   if (items <= 8) return launch_rescore_t<8>(p, stream);
