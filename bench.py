@@ -343,6 +343,27 @@ def main():
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
 
+    # result quality, outside the timed regions: this mode's neighbours and predictions for a
+    # sample of the batch against the on-device exact mode (sequential-fma fp32, bit-checked
+    # against the oracle by tests/): recall@k, and bitwise key equality for the fp32-matching modes
+    quality = None
+    rescore_stats, prepass_stats = dict(K.last_rescore_stats), dict(K.last_prepass_stats)
+    if world == 1 and mode != "exact":
+        nq = min(Q, 256)
+        qs = q[:nq].contiguous()
+        ek = b200knn.topk_keys(qs, bank, KNN_K, mode="exact")
+        tk = b200knn.topk_keys(qs, bank, KNN_K, mode=mode)
+        ei = b200knn.decode_keys(ek)[1].cpu().numpy()
+        ti = b200knn.decode_keys(tk)[1].cpu().numpy()
+        recall = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ei, ti)) / float(nq * KNN_K)
+        b200knn.set_default_mode("exact")
+        pe = b200knn.knn_predict(qs, bank, labels, N_CLASSES, KNN_K, KNN_T)
+        b200knn.set_default_mode(mode)
+        pm = b200knn.knn_predict(qs, bank, labels, N_CLASSES, KNN_K, KNN_T)
+        quality = {"sample_queries": nq, "recall_at_k": recall, "keys_bitwise_equal_exact_mode": bool(torch.equal(ek, tk)),
+                   "top1_agreement_with_exact_mode": float((pe[:, 0] == pm[:, 0]).float().mean().item()),
+                   "class_ranking_equal_exact_mode": bool(torch.equal(pe, pm))}
+
     phases = None
     if world > 1:  # where a sharded step spends its time (one extra untimed step, rank 0's view)
         sb.phase_log = []
@@ -370,9 +391,17 @@ def main():
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                     "frac": achieved / pk["bf16"], "executed_frac": 3 * achieved / pk["bf16"],
                     "traffic": None, "kernel": "tc_topk_kernel<BF16X3,128> candidates (3 bf16 MMAs per k-step)"
-                    + (" + rescore_kernel" if mode in K.RESCORED_MODES else ""),
+                    + (" + rescore_dot_kernel" if mode in K.RESCORED_MODES else ""),
                     "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json); frac counts the useful "
                                    "2*N*D flops per query, executed_frac the 3 MMAs actually issued", "kernel_ms": kern}
+        elif cand_mode == "f16x2":
+            roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["bf16"], "executed_frac": 2 * achieved / pk["bf16"],
+                    "traffic": None, "kernel": "tc_topk_kernel<F16X2,256,cta_group::2> candidates (2 fp16 MMAs per k-step)"
+                    + (" + rescore_dot_kernel" if mode in K.RESCORED_MODES else ""),
+                    "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json; fp16 runs at the bf16 rate); frac "
+                                   "counts the useful 2*N*D flops per query, executed_frac the 2 MMAs actually issued",
+                    "kernel_ms": kern}
         elif cand_mode == "tf32x3":
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"] / 2, "unit": "TFLOP/s",
                     "frac": achieved / (pk["bf16"] / 2), "executed_frac": 3 * achieved / (pk["bf16"] / 2),
@@ -399,12 +428,13 @@ def main():
             "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "exact": "f32", "fp32": "bf16x3+f32",
-                      "fp32_bf16x3": "bf16x3+f32", "fp32_tf32": "tf32x3+f32", "fp32_bf16": "bf16+f32"}[mode], "data": "synthetic",
+            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "f16x2": "f16x2", "exact": "f32",
+                      "fp32": "f16x2+f32", "fp32_f16x2": "f16x2+f32", "fp32_bf16x3": "bf16x3+f32",
+                      "fp32_tf32": "tf32x3+f32", "fp32_bf16": "bf16+f32"}[mode], "data": "synthetic",
             "config": {"workload": f"knn_predict N={N} D={DIM} k={KNN_K} t={KNN_T} C={N_CLASSES}; "
                                    f"Q={Q} queries per step (clustered synthetic, WM-811K class priors)",
                        "mode": mode, "bank_sharding": f"row-sharded over {world} GPU(s)" if world > 1 else "none",
-                       "l2": "inputs larger than L2 (prepared bank %.0f MB)" % (n_local * DIM * {"bf16": 2, "bf16x3": 4, "tf32x3": 8, "exact": 4}[cand_mode] / 1e6),
+                       "l2": "inputs larger than L2 (prepared bank %.0f MB)" % (n_local * DIM * {"bf16": 2, "bf16x3": 4, "f16x2": 4, "tf32x3": 8, "exact": 4}[cand_mode] / 1e6),
                        "plan": plan, "bank_prepare_ms_excluded": prepare_ms},
             "roofline": roof,
             "e2e": {"value": Q / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",
@@ -414,13 +444,15 @@ def main():
             "gpu_launches": gpu_launches,
             "clocks": clocks.summary(),
         }
+        if quality is not None:
+            line["quality"] = quality
         if phases is not None:
             line["config"]["phases_ms"] = phases
             line["config"]["exchange"] = "all-to-all of (B,k) keys by query slice + all-gather of (B,C) rankings (NCCL)"
         if mode in K.RESCORED_MODES:
-            line["config"]["uncertified_rows_last_step"] = K.last_rescore_stats["uncertified"]
+            line["config"]["uncertified_rows_last_step"] = rescore_stats["uncertified"]
         line["config"]["prepass"] = {"stride": K.prepass_stride(N, k_plan), "r": K.PREPASS["r"],
-                                     "repaired_rows_last_step": K.last_prepass_stats["repaired"]}
+                                     "repaired_rows_last_step": prepass_stats["repaired"]}
         if world == 1 and not args.no_cpu_baseline:
             rate, times, threads = cpu_reference_rate(1024, 12)
             line["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": threads, "kind": "port",

@@ -58,6 +58,10 @@ extern "C" {
 #define B200KNN_MODE_F32ROWS 3 /* b200knn_prepare_rows only: plain fp32 (n_vec, dim_pad) row-major copy */
 #define B200KNN_MODE_BF16X3 4 /* tcgen05 kind::f16, bf16 hi/lo split operands, 3 MMAs per k-step:
                                  ~2^-16 relative operand error at twice the TF32X3 MMA rate */
+#define B200KNN_MODE_F16X2 5 /* tcgen05 kind::f16, fp16 queries (one array) x fp16 hi/lo split bank, 2 MMAs per
+                               k-step: one-sided operand error 2^-11 ||q|| ||x|| (+ 2^-25 per element below the
+                               fp16 normal range); values beyond +-65504 saturate.  Candidate generator of the
+                               "fp32" cascade (b200knn_rescore certifies with err_abs / max_abs). */
 
 int b200knn_version(void);
 const char* b200knn_last_error(void);

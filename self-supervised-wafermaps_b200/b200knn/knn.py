@@ -32,7 +32,7 @@ from . import _lib
 
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
-TC_MODES = ("bf16", "tf32x3", "bf16x3")  # raw tensor-core similarity modes
+TC_MODES = ("bf16", "tf32x3", "bf16x3", "f16x2")  # raw tensor-core similarity modes
 MAX_K = 992  # largest k of the streaming candidate lists (capacity 1024, include/b200knn.h)
 MAX_BF16_DIM = 768  # widest (padded) vector whose query tile the BF16 kernel can keep resident
 
@@ -57,14 +57,24 @@ profile_events = None
 #   bf16x3: operands hi + lo with |x - hi - lo| <= 2^-16 |x| each and the dropped lo*lo term
 #           (2^-16): 3 * 2^-16 = 4.6e-5 is rigorous; 6e-5 leaves the same empirical allowance for
 #           the accumulation as tf32x3.
+#   f16x2 : fp16 queries x (fp16 hi + fp16 lo) bank, two MMAs per k-step.  Rigorous operand part:
+#           |q_i - fp16(q_i)| <= 2^-11 |q_i| + 2^-25 and |x_i - hi_i - lo_i| <= 2^-22 |x_i| + 2^-25
+#           (the 2^-25 terms cover fp16's subnormal range), hence
+#           |error| <= (2^-11 + 2^-22) ||q|| ||x|| + 2^-25 sqrt(D) (||q|| + ||x||)  = err_coef, err_abs;
+#           2e-5 is the same empirical accumulation allowance as above.  Operands at or beyond
+#           fp16's range (max_abs) are refused.  The one-sided 2^-11 needs k+40 candidates where the
+#           split modes need k+16, and buys a third fewer MMAs than bf16x3 on CTA pairs.
 LEVELS = {
+    "fp32_f16x2": dict(cand="f16x2", margin=40, err_coef=1.001 * (2.0 ** -11 + 2.0 ** -22) + 2e-5,
+                       err_abs=1.01 * 2.0 ** -25, max_abs=6.0e4),
     "fp32_bf16": dict(cand="bf16", margin=128, err_coef=1.02 * 2.0 ** -7),
     "fp32_bf16x3": dict(cand="bf16x3", margin=16, err_coef=6e-5),
     "fp32_tf32": dict(cand="tf32x3", margin=8, err_coef=2e-5),
 }
 # mode -> levels tried in order (then "exact").  "fp32" skips its BF16 level for a bank on which
 # that level recently left more than CASCADE_GIVE_UP of the rows uncertified.
-CASCADES = {"fp32": ("fp32_bf16x3", "fp32_tf32"), "fp32_bf16x3": ("fp32_bf16x3",),
+CASCADES = {"fp32": ("fp32_f16x2", "fp32_bf16x3", "fp32_tf32"), "fp32_f16x2": ("fp32_f16x2",),
+            "fp32_bf16x3": ("fp32_bf16x3",),
             "fp32_bf16": ("fp32_bf16",), "fp32_tf32": ("fp32_tf32",)}
 CASCADE_GIVE_UP = 0.25
 CASCADE_RETRY_CALLS = 64
@@ -80,10 +90,12 @@ def set_default_mode(mode: str) -> None:
     """Select the similarity mode ``knn_predict``/``knn_topk`` use when none is passed.
 
     ``"exact"``     fp32 CUDA-core contraction, sequential-fma similarities (bitwise reproducible);
-    ``"fp32"``      tensor-core candidates + exact re-scoring + certificate, cascading split-BF16
-                    (3 MMAs, k+16 candidates) -> 3xTF32 (k+8) -> exact for the rows each level cannot
-                    certify: bitwise the ``"exact"`` result at tensor-core speed (the fp32-matching mode);
-    ``"fp32_bf16x3"`` / ``"fp32_tf32"`` / ``"fp32_bf16"``  a single level (then exact);
+    ``"fp32"``      tensor-core candidates + exact re-scoring + certificate, cascading fp16 x split-fp16
+                    (2 MMAs, k+40 candidates) -> split-BF16 (3 MMAs, k+16) -> 3xTF32 (k+8) -> exact for
+                    the rows each level cannot certify: bitwise the ``"exact"`` result at tensor-core
+                    speed (the fp32-matching mode);
+    ``"fp32_f16x2"`` / ``"fp32_bf16x3"`` / ``"fp32_tf32"`` / ``"fp32_bf16"``  a single level (then exact);
+    ``"f16x2"``     raw tcgen05 fp16 x (fp16 hi + lo) similarities (~2.5e-4 relative to ||q|| ||x||);
     ``"bf16x3"``    raw tcgen05 bf16 hi/lo-split similarities (~1e-5 relative);
     ``"tf32x3"``    raw tcgen05 hi/lo-split TF32 similarities (fp32-class accuracy, ~1e-6);
     ``"bf16"``      raw tcgen05 BF16 operands / fp32 accumulate (fastest; recall@k reported by bench).
@@ -238,6 +250,9 @@ def prepare_rows(x: torch.Tensor, mode: str, vectors_are_columns: bool) -> Prepa
     elif mode == "bf16x3":
         hi = torch.empty((n, dpad), dtype=torch.bfloat16, device=x.device)
         lo = torch.empty((n, dpad), dtype=torch.bfloat16, device=x.device)
+    elif mode == "f16x2":  # queries: one fp16 array; bank: hi + lo
+        hi = torch.empty((n, dpad), dtype=torch.float16, device=x.device)
+        lo = torch.empty((n, dpad), dtype=torch.float16, device=x.device) if vectors_are_columns else None
     elif mode == "f32rows":
         hi = torch.empty((n, dpad), dtype=torch.float32, device=x.device)
         lo = None
@@ -460,8 +475,8 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
         raise ValueError(f"unknown mode {mode!r}")
     _check_feature_bank(feature, feature_bank)
     B, D = feature.shape
-    if mode == "bf16" and padded_dim(D) > MAX_BF16_DIM:
-        # the BF16 kernel keeps a 128-row query tile resident in shared memory (D_pad * 256 B);
+    if mode in ("bf16", "f16x2") and padded_dim(D) > MAX_BF16_DIM:
+        # these kernels keep a 128-row query tile resident in shared memory (D_pad * 256 B);
         # wider vectors go through the split kernel, which streams both operands
         mode = "bf16x3"
     N = feature_bank.shape[1]
@@ -621,6 +636,8 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
 
 def _cascade_levels(feature_bank: torch.Tensor, mode: str):
     levels = list(CASCADES[mode])
+    if len(levels) > 1 and levels[0] == "fp32_f16x2" and padded_dim(feature_bank.shape[0]) > MAX_BF16_DIM:
+        levels = levels[1:]  # no resident query tile at this width: start at the split-BF16 level
     if len(levels) > 1:
         st = bank_cache.state(feature_bank)
         if st.get("skip_first", 0) > 0:

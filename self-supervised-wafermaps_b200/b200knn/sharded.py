@@ -28,6 +28,8 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
+_TC_MODES = ("bf16", "tf32x3", "bf16x3", "f16x2")  # = knn.TC_MODES (raw tensor-core similarity modes)
+
 
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Rows [lo, hi) of the bank owned by `rank` (contiguous, ceil-divided)."""
@@ -49,7 +51,7 @@ class _CudaOps:
     def topk_into(feature, bank_shard, k, mode, idx_offset, tau0, out):
         """topk_keys writing into `out` when the mode allows it (tensor-core mode with a threshold)."""
         from .knn import topk_keys
-        if tau0 is not None and mode in ("bf16", "tf32x3", "bf16x3"):
+        if tau0 is not None and mode in _TC_MODES:
             topk_keys(feature, bank_shard, k, mode, idx_offset, tau0, out=out)
         else:
             out.copy_(topk_keys(feature, bank_shard, k, mode, idx_offset, tau0))
@@ -156,7 +158,7 @@ class ShardedBank:
         sample of the WHOLE bank — becomes the same admission threshold on every rank.  Shards
         then only collect rows that can still reach the global top-k, so the per-shard work no
         longer carries a fixed list warm-up (this is what lets the sharded mode scale)."""
-        if self.mode not in ("bf16", "tf32x3", "bf16x3") or self.world_size == 1:
+        if self.mode not in _TC_MODES or self.world_size == 1:
             return None
         sk = self.ops.sample_keys(feature, self.bank_shard, k, self.mode, self.n_rows)
         if sk is None:
@@ -245,7 +247,7 @@ class ShardedBank:
         all-to-all overlaps the remaining tiles' math.  Returns None when not applicable."""
         if not (self.fused_exchange and feature.is_cuda and hasattr(self.ops, "topk_scatter")):
             return None
-        if self.world_size > 8 or self.mode not in ("bf16", "tf32x3", "bf16x3"):
+        if self.world_size > 8 or self.mode not in _TC_MODES:
             return None
         # the decision must be the same on every rank: check every shard's size and work plan
         B, D = feature.shape

@@ -29,6 +29,11 @@ int sm_count() {
   return n;
 }
 
+bool is_tc_mode(int mode) {
+  return mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_TF32X3 || mode == B200KNN_MODE_BF16X3 ||
+         mode == B200KNN_MODE_F16X2;
+}
+
 bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan* plan) {
   const int cap = b200knn::list_capacity(k);
   if (cap == 0) return false;
@@ -66,8 +71,8 @@ int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout, int64_t
   if (src_layout != B200KNN_LAYOUT_DN && src_layout != B200KNN_LAYOUT_ND)
     return fail(B200KNN_E_ARG, "prepare_rows: unknown layout");
   if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_F32ROWS &&
-      mode != B200KNN_MODE_BF16X3)
-    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16, TF32X3, BF16X3 or F32ROWS");
+      mode != B200KNN_MODE_BF16X3 && mode != B200KNN_MODE_F16X2)
+    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16, TF32X3, BF16X3, F16X2 or F32ROWS");
   if ((mode == B200KNN_MODE_TF32X3 || mode == B200KNN_MODE_BF16X3) && !dst_lo)
     return fail(B200KNN_E_ARG, "prepare_rows: split modes need dst_lo");
   cudaError_t e = b200knn::launch_prepare(src, src_dtype, src_layout, n_vec, dim, ld, mode, dst_hi,
@@ -137,8 +142,8 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.out = partial;
     e = b200knn::launch_exact(p, plan.grid, plan.cap, st);
     if (e != cudaSuccess) return fail_cuda("topk(exact)", e);
-  } else if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_TF32X3 || mode == B200KNN_MODE_BF16X3) {
-    if (mode != B200KNN_MODE_BF16 && (!q_lo || !bank_lo))
+  } else if (is_tc_mode(mode)) {
+    if (mode == B200KNN_MODE_F16X2 ? !bank_lo : (mode != B200KNN_MODE_BF16 && (!q_lo || !bank_lo)))
       return fail(B200KNN_E_ARG, "topk: split modes need the lo operands");
     b200knn::TcParams p;
     p.mode = mode;
@@ -194,8 +199,7 @@ int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo, const void* ba
                     const void* bank_lo, int64_t B, int64_t n_visit, int dim, int k, int64_t idx_offset,
                     int64_t bank_row_stride, const float* tau0, uint64_t* out_keys, void* workspace,
                     size_t workspace_bytes, void* stream) {
-  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_BF16X3)
-    return fail(B200KNN_E_ARG, "topk_ex: tensor-core modes only");
+  if (!is_tc_mode(mode)) return fail(B200KNN_E_ARG, "topk_ex: tensor-core modes only");
   if (bank_row_stride < 1) return fail(B200KNN_E_ARG, "topk_ex: bank_row_stride must be >= 1");
   return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, k, idx_offset,
                    out_keys, workspace, workspace_bytes, stream, nullptr, nullptr, 0, bank_row_stride,
@@ -206,8 +210,7 @@ int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo, const void
                         const void* bank_lo, int64_t B, int64_t n_visit, int dim,
                         int64_t bank_row_stride, uint64_t* out_keys, void* workspace,
                         size_t workspace_bytes, void* stream) {
-  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_BF16X3)
-    return fail(B200KNN_E_ARG, "topk_sample: tensor-core modes only");
+  if (!is_tc_mode(mode)) return fail(B200KNN_E_ARG, "topk_sample: tensor-core modes only");
   if (bank_row_stride < 1) return fail(B200KNN_E_ARG, "topk_sample: bank_row_stride must be >= 1");
   if (n_visit < B200KNN_SAMPLE_R) return fail(B200KNN_E_ARG, "topk_sample: fewer than 16 rows to sample");
   return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, B200KNN_SAMPLE_R, 0,
@@ -219,8 +222,7 @@ int b200knn_topk_scatter(int mode, const void* q_hi, const void* q_lo, const voi
                          const void* bank_lo, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
                          const float* tau0, const void* const* host_peer_out, int n_peers, int my_rank,
                          int64_t rows_per_owner, void* workspace, size_t workspace_bytes, void* stream) {
-  if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_BF16X3)
-    return fail(B200KNN_E_ARG, "topk_scatter: tensor-core modes only");
+  if (!is_tc_mode(mode)) return fail(B200KNN_E_ARG, "topk_scatter: tensor-core modes only");
   if (!host_peer_out || n_peers < 1 || n_peers > 8 || my_rank < 0 || my_rank >= n_peers)
     return fail(B200KNN_E_ARG, "topk_scatter: 1..8 peers and a rank among them");
   if (rows_per_owner <= 0 || rows_per_owner * n_peers < B)

@@ -26,6 +26,11 @@
 // MODE_BF16  : operands bf16 K-major, kind::f16, UMMA 128 x BLOCK_N x 16.
 // MODE_BF16X3: operands bf16 hi/lo split (prepare.cu), kind::f16; same three products per
 //              k-step as TF32X3 at twice its MMA rate (~2^-16 relative operand error).
+// MODE_F16X2 : queries fp16 (one array, resident like BF16), bank fp16 hi/lo split; per k-block
+//              q*lo + q*hi, the two bank arrays streamed as alternating pipeline stages.  Runs
+//              as CTA pairs like BF16: two MMAs per k-step instead of BF16X3's three, one-sided
+//              operand error 2^-11 (the query rounding) — candidate generator of the default
+//              "fp32" cascade.
 // MODE_TF32X3: operands fp32 hi/lo split (prepare.cu), kind::tf32, UMMA
 //              128 x BLOCK_N x 8; per k-step  hi*lo + lo*hi + hi*hi  accumulate
 //              into the same TMEM tile; A and B are both streamed per k-block.
@@ -43,7 +48,7 @@
 namespace b200knn {
 
 int tc_tile_n(int mode, int dim) {
-  if (mode == B200KNN_MODE_BF16) return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
+  if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16X2) return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
   return 128;
 }
 
@@ -54,7 +59,7 @@ bool tc_use_pair(int mode) {
     const char* e = getenv("B200KNN_NO_PAIR");
     no_pair = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  return mode == B200KNN_MODE_BF16 && no_pair == 0;
+  return (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16X2) && no_pair == 0;
 }
 
 namespace {
@@ -128,9 +133,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                    const __grid_constant__ CUtensorMap map_q_lo,
                    const __grid_constant__ CUtensorMap map_b_hi,
                    const __grid_constant__ CUtensorMap map_b_lo, const TcKernelArgs a) {
-  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);     // one operand pair, query tile resident
+  // query tile resident in smem, only bank tiles are streamed (BF16, F16X2)
+  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16 || MODE == B200KNN_MODE_F16X2);
+  constexpr int kBArrays = (MODE == B200KNN_MODE_F16X2) ? 2 : 1;  // bank arrays streamed per k-block (lo, hi)
   constexpr bool kHalf = (MODE != B200KNN_MODE_TF32X3);   // 2-byte elements (kind::f16)
-  static_assert(!PAIR || kBf16, "CTA pairs are implemented for the BF16 mode");
+  static_assert(!PAIR || kBf16, "CTA pairs are implemented for the resident-query modes");
   constexpr int CAP = ITEMS * 32;
   constexpr int kCtas = PAIR ? 2 : 1;
   constexpr int kBRows = BLOCK_N / kCtas;  // bank rows of one tile this CTA loads
@@ -138,7 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kStageBytes = kBf16 ? kBBlockBytes : 2 * (kABlockBytes + kBBlockBytes);
   constexpr int kElemsPerRow = kHalf ? 64 : 32;  // elements of one 128-byte k-block row
   constexpr int kUmmaKBytes = 32;                // one MMA consumes 32 bytes of k per row
-  constexpr uint32_t kIdesc = ptx::make_idesc(kHalf ? 1u : 2u, kTileM * kCtas, BLOCK_N);
+  constexpr uint32_t kIdesc =
+      ptx::make_idesc(MODE == B200KNN_MODE_F16X2 ? 0u : (kHalf ? 1u : 2u), kTileM * kCtas, BLOCK_N);
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -161,10 +169,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_q_hi);
     ptx::prefetch_tensormap(&map_b_hi);
-    if (!kBf16) {
-      ptx::prefetch_tensormap(&map_q_lo);
-      ptx::prefetch_tensormap(&map_b_lo);
-    }
+    if (!kBf16) ptx::prefetch_tensormap(&map_q_lo);
+    if (!kBf16 || kBArrays == 2) ptx::prefetch_tensormap(&map_b_lo);
     for (int s = 0; s < a.n_stages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->empty[s]), 1);
@@ -222,7 +228,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
           const int nrow = int(n0) + int(cta_rank) * kBRows;  // this CTA's half of the bank tile
-          for (int kb = 0; kb < a.n_kblocks; ++kb) {
+          // resident-query modes: one pipeline stage per (k-block, bank array); F16X2 visits lo, hi
+          for (int v = 0; v < a.n_kblocks * kBArrays; ++v) {
+            const int kb = v / kBArrays;
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, a.diag, 2);
             if (ptx::elect_one()) {
               const uint32_t full = ptx::smem_u32(&bars->full[stage]);
@@ -230,11 +238,12 @@ __global__ void __launch_bounds__(kThreads, 1)
               if (DEBUG && (a.flags & 8)) {
                 if (leader) ptx::mbar_arrive(full);
               } else if (kBf16) {
+                const CUtensorMap* mb = (kBArrays == 2 && (v & 1) == 0) ? &map_b_lo : &map_b_hi;
                 if (leader) ptx::mbar_expect_tx(full, uint32_t(kStageBytes) * kCtas);
                 if (PAIR)
-                  ptx::tma_load_2d_pair(st, &map_b_hi, kb * kElemsPerRow, nrow, ptx::mapa(full, 0));
+                  ptx::tma_load_2d_pair(st, mb, kb * kElemsPerRow, nrow, ptx::mapa(full, 0));
                 else
-                  ptx::tma_load_2d(st, &map_b_hi, kb * kElemsPerRow, nrow, full);
+                  ptx::tma_load_2d(st, mb, kb * kElemsPerRow, nrow, full);
               } else {
                 ptx::mbar_expect_tx(full, uint32_t(kStageBytes));
                 ptx::tma_load_2d(st, &map_q_hi, kb * kElemsPerRow, m0, full);
@@ -276,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[buf]), aphase ^ 1, a.diag, 4);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
-          for (int kb = 0; kb < a.n_kblocks; ++kb) {
+          for (int v = 0; v < a.n_kblocks * kBArrays; ++v) {
+            const int kb = v / kBArrays;
             ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase, a.diag, 5);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
@@ -289,9 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int ks = 0; ks < kRowBytes / kUmmaKBytes; ++ks) {
                   const uint64_t o = uint64_t((ks * kUmmaKBytes) >> 4);
                   if (PAIR)
-                    ptx::umma_f16_pair(tmem_d, da + o, db + o, kIdesc, uint32_t((kb | ks) != 0));
+                    ptx::umma_f16_pair(tmem_d, da + o, db + o, kIdesc, uint32_t((v | ks) != 0));
                   else
-                    ptx::umma_f16(tmem_d, da + o, db + o, kIdesc, uint32_t((kb | ks) != 0));
+                    ptx::umma_f16(tmem_d, da + o, db + o, kIdesc, uint32_t((v | ks) != 0));
                 }
               } else {
                 const uint64_t a_hi = desc0 + uint64_t((st & 0x3FFFFu) >> 4);
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               // frees the smem stage (in both CTAs of a pair)
               if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->empty[stage]), 3);
               else ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
-              if (kb + 1 == a.n_kblocks) {  // accumulator ready
+              if (v + 1 == a.n_kblocks * kBArrays) {  // accumulator ready
                 if (PAIR) ptx::umma_commit_pair(ptx::smem_u32(&bars->tmem_full[buf]), 3);
                 else ptx::umma_commit(ptx::smem_u32(&bars->tmem_full[buf]));
               }
@@ -525,7 +535,7 @@ EncodeTiledFn get_encode() {
 
 // rows x cols matrix of `esize`-byte elements, row pitch = cols*esize; box = box_rows x 128 bytes
 bool make_map(CUtensorMap* m, const void* base, bool bf16, uint64_t rows, uint64_t cols,
-              uint32_t box_rows, uint64_t row_stride = 1) {
+              uint32_t box_rows, uint64_t row_stride = 1, bool fp16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   const uint64_t esize = bf16 ? 2 : 4;
@@ -533,7 +543,8 @@ bool make_map(CUtensorMap* m, const void* base, bool bf16, uint64_t rows, uint64
   cuuint64_t gstride[1] = {cols * esize * row_stride};  // row_stride > 1: every row_stride-th row
   cuuint32_t box[2] = {cuuint32_t(kRowBytes / esize), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                        : (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2,
                    const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -543,7 +554,8 @@ bool make_map(CUtensorMap* m, const void* base, bool bf16, uint64_t rows, uint64
 template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG, bool PAIR, bool SAMPLE = false>
 cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* dump, int32_t* diag,
                      int flags, const char** why) {
-  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16);
+  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16 || MODE == B200KNN_MODE_F16X2);  // resident query tile
+  constexpr bool kF16 = (MODE == B200KNN_MODE_F16X2);
   constexpr bool kHalf = (MODE != B200KNN_MODE_TF32X3);
   constexpr int kCtas = PAIR ? 2 : 1;
   constexpr int kBRows = BLOCK_N / kCtas;
@@ -582,19 +594,17 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   const size_t smem = size_t(fixed) + size_t(stages) * stage_bytes;
 
   CUtensorMap mq_hi, mq_lo, mb_hi, mb_lo;
-  bool ok = make_map(&mq_hi, p.q_hi, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-            make_map(&mb_hi, p.bank_hi, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
-  if (ok && !kBf16)
-    ok = make_map(&mq_lo, p.q_lo, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM) &&
-         make_map(&mb_lo, p.bank_lo, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride));
+  bool ok = make_map(&mq_hi, p.q_hi, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM, 1, kF16) &&
+            make_map(&mb_hi, p.bank_hi, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride), kF16);
+  if (ok && !kBf16) ok = make_map(&mq_lo, p.q_lo, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM);
+  if (ok && (!kBf16 || kF16))
+    ok = make_map(&mb_lo, p.bank_lo, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride), kF16);
   if (!ok) {
     *why = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
-  if (kBf16) {
-    mq_lo = mq_hi;
-    mb_lo = mb_hi;
-  }
+  if (kBf16) mq_lo = mq_hi;
+  if (kBf16 && !kF16) mb_lo = mb_hi;
   auto kern = tc_topk_kernel<MODE, BLOCK_N, ITEMS, DEBUG, PAIR, SAMPLE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
@@ -645,6 +655,15 @@ cudaError_t launch_mode(const TcParams& p, int grid, int cap, cudaStream_t strea
     }
     if (wide) return launch_cap<B200KNN_MODE_BF16, 256, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
     return launch_cap<B200KNN_MODE_BF16, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
+  }
+  if (p.mode == B200KNN_MODE_F16X2) {
+    const bool wide = tc_tile_n(p.mode, p.D) == 256;
+    if (tc_use_pair(p.mode)) {
+      if (wide) return launch_cap<B200KNN_MODE_F16X2, 256, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
+      return launch_cap<B200KNN_MODE_F16X2, 128, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
+    }
+    if (wide) return launch_cap<B200KNN_MODE_F16X2, 256, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
+    return launch_cap<B200KNN_MODE_F16X2, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
   }
   if (p.mode == B200KNN_MODE_TF32X3)
     return launch_cap<B200KNN_MODE_TF32X3, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);

@@ -55,7 +55,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3", "f16x2"])
 @pytest.mark.parametrize("name,_", CASES)
 def test_tiles_and_selection(name, _, mode):
     c = datagen.make_case(name)
@@ -68,6 +68,20 @@ def test_tiles_and_selection(name, _, mode):
         bh = pb.hi.float().cpu().numpy()[:, :D].astype(np.float64)
         ref = qh @ bh.T
         tol = 2e-6  # fp32 accumulation of exact bf16 products
+    elif mode == "f16x2":
+        # fp16 queries (one array) x fp16 hi + lo bank: products are exact in fp32, 2 MMAs per k-step
+        assert pq.lo is None
+        qh = pq.hi.double().cpu().numpy()[:, :D]
+        bf = (pb.hi.double() + pb.lo.double()).cpu().numpy()[:, :D]
+        assert (np.abs(qh - q) <= 2.0 ** -11 * np.abs(q) + 2.0 ** -25).all()
+        assert (np.abs(bf - bank.T) <= 2.0 ** -22 * np.abs(bank.T) + 2.0 ** -25).all()
+        ref = qh @ bf.T
+        qn, bn = np.linalg.norm(q, axis=1).max(), np.linalg.norm(bank, axis=0).max()
+        tol = 4e-6 * max(1.0, qn * bn)
+        # and against the true similarities: the certificate bound of level fp32_f16x2
+        lv = K.LEVELS["fp32_f16x2"]
+        bound = lv["err_coef"] * qn * bn + lv["err_abs"] * np.sqrt(K.padded_dim(D)) * (qn + bn)
+        assert np.abs(dump.astype(np.float64) - q.astype(np.float64) @ bank.astype(np.float64)).max() <= bound
     elif mode == "bf16x3":
         # hi + lo carries 16 mantissa bits: |x - hi - lo| <= 2^-16 |x|; the kernel drops lo*lo
         qf = (pq.hi.double() + pq.lo.double()).cpu().numpy()[:, :D]
@@ -106,7 +120,7 @@ def test_tf32x3_raw_accuracy(name):
     assert r["recall_at_k"] >= 0.999
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_f16x2", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
 @pytest.mark.parametrize("name", datagen.CASE_NAMES)
 def test_fp32_modes_bitwise_equal_exact_and_oracle(name, mode):
     """The fp32-matching modes (tensor-core candidates + exact re-scoring + certificate) must give
@@ -131,7 +145,7 @@ def test_fp32_modes_bitwise_equal_exact_and_oracle(name, mode):
         assert stats["uncertified"] <= max(1, stats["rows"] // 10)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_f16x2", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
 @pytest.mark.parametrize("model", ["FastSiam", "SimSiam"])
 def test_fp32_modes_real_banks(model, mode, golden_dir):
     """Duplicates, 80 % exact zeros, row norms up to 277 (un-normalised): certificate + fallback
@@ -163,7 +177,7 @@ def test_bf16_recall(name):
     assert r["recall_at_k"] >= 0.98 and r["max_rel_err"] <= 2e-2
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3", "fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3", "f16x2", "fp32", "fp32_f16x2", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"])
 def test_large_bank_against_exact_mode(mode):
     """Sizes the CPU oracle cannot cover: tensor-core modes against the on-device exact mode
     (itself bit-checked against the oracle in test_gpu_exact.py) on a 811,457 x 512 bank."""
@@ -178,7 +192,7 @@ def test_large_bank_against_exact_mode(mode):
     ei, ti = ei.cpu().numpy(), ti.cpu().numpy()
     recall = np.mean([len(set(ei[b]) & set(ti[b])) / k for b in range(B)])
     print(f"{mode} recall@{k} vs exact at N={N}: {recall:.5f}")
-    if mode in ("fp32", "fp32_bf16x3", "fp32_bf16", "fp32_tf32"):
+    if mode in K.RESCORED_MODES:
         print(f"   uncertified rows {K.last_rescore_stats['uncertified']}/{K.last_rescore_stats['rows']}")
         assert torch.equal(ek, tk)  # bitwise: indices, similarities, order
     elif mode in ("tf32x3", "bf16x3"):
@@ -186,11 +200,13 @@ def test_large_bank_against_exact_mode(mode):
         # batch invariance of the tensor-core path: same rows, smaller batch, identical keys
         tk2 = b200knn.topk_keys(q[:64].contiguous(), bank, k, mode=mode)
         assert torch.equal(tk2, tk[:64])
+    elif mode == "f16x2":
+        assert recall >= 0.99 and float((es - ts).abs().max()) <= 5.2e-4
     else:
         assert recall >= 0.98
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32x3", "bf16x3", "f16x2"])
 def test_prepass_threshold_does_not_change_results(mode):
     """The sampling pre-pass only supplies a starting threshold: keys with it on and off must be
     bitwise identical (and the repair path must be a no-op or fix every row)."""
@@ -252,7 +268,7 @@ def test_register_sample_is_a_valid_threshold(mode, B, N, stride):
 
 
 @pytest.mark.parametrize("D", [200, 768, 1024])
-@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "f16x2", "fp32"])
 def test_other_vector_dims(D, mode):
     """D=768 is config c5 (BASELINE.json), D=200 exercises the zero-padded last k-block, D=1024 the
     route around the resident query tile; checked against the on-device exact mode."""
@@ -273,11 +289,13 @@ def test_other_vector_dims(D, mode):
     print(f"D={D} {mode}: recall@{k} {recall:.4f}, max |sim - exact| {err:.2e}")
     if mode == "bf16" and D <= 768:
         assert recall >= 0.95 and err <= 1e-2
+    elif mode == "f16x2" and D <= 768:  # wider vectors are routed to bf16x3
+        assert recall >= 0.99 and err <= 5.2e-4
     else:
         assert recall >= 0.995 and err <= 6e-5
 
 
-@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "f16x2", "fp32"])
 def test_tie_flood_and_degenerate_banks(mode):
     """All similarities equal (identical bank rows, or a zero query): the radix-select prune cannot
     separate anything and must hand over to the exact sort; order is then by lowest index."""
@@ -301,7 +319,7 @@ def test_tie_flood_and_degenerate_banks(mode):
     assert torch.equal(s2[:, 0::2], s2[:, 1::2])
 
 
-@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "fp32", "exact"])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "tf32x3", "f16x2", "fp32", "exact"])
 @pytest.mark.parametrize("B,N,k", [(1, 200, 200), (3, 257, 1), (129, 300, 300), (64, 1500, 992), (2, 17, 5)])
 def test_small_and_extreme_shapes(mode, B, N, k):
     """k = N (every row is a neighbour), one query, banks smaller than one tile, the largest k."""
@@ -321,7 +339,7 @@ def test_small_and_extreme_shapes(mode, B, N, k):
         assert bool((ti >= 0).all()) and bool((ti < N).all())
         if k == N:  # every row must appear exactly once
             assert torch.equal(torch.sort(ti, dim=1).values, torch.arange(N, device=DEV).expand(B, N))
-        tol = {"bf16": 0.3, "bf16x3": 2e-3, "tf32x3": 5e-4}[mode]
+        tol = {"bf16": 0.3, "bf16x3": 2e-3, "tf32x3": 5e-4, "f16x2": 0.1}[mode]
         assert float((ts[:, 0] - es[:, 0]).abs().max()) <= tol
 
 
