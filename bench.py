@@ -63,6 +63,8 @@ def make_inputs(device, n_bank, n_query, dim, seed, row_range=None):
 
     g0 = torch.Generator(device=device).manual_seed(seed)
     prior = torch.tensor([859, 111, 1037, 1936, 719, 30, 173, 239, 7345], dtype=torch.float64, device=device)
+    if N_CLASSES != 9:  # MixedWM38 (config c3): flat prior
+        prior = torch.ones(N_CLASSES, dtype=torch.float64, device=device)
     cent = torch.nn.functional.normalize(torch.randn(N_CLASSES, dim, generator=g0, device=device), dim=1)
     lo_own, hi_own = row_range if row_range is not None else (0, n_bank)
 
@@ -190,7 +192,7 @@ def run_reference(args):
 
 
 def main():
-    global DIM, KNN_K, N_BANK
+    global DIM, KNN_K, N_BANK, N_CLASSES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -200,10 +202,12 @@ def main():
     ap.add_argument("--queries", type=int, default=4 * WAVE, help="queries per step (default 75,776 = 4 waves)")
     ap.add_argument("--bank", type=int, default=N_BANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-line", action="store_true", help="skip the secondary measurement of the bit-exact mode")
     ap.add_argument("--dim", type=int, default=DIM, help="vector dimension (default 512; 768 = config c5)")
     ap.add_argument("--k", type=int, default=KNN_K)
+    ap.add_argument("--classes", type=int, default=N_CLASSES, help="9 = WM-811K priors; 38 = MixedWM38 (config c3)")
     args = ap.parse_args()
-    DIM, KNN_K, N_BANK = args.dim, args.k, args.bank
+    DIM, KNN_K, N_BANK, N_CLASSES = args.dim, args.k, args.bank, args.classes
     if args.impl == "reference":
         return run_reference(args)
 
@@ -364,6 +368,25 @@ def main():
                    "top1_agreement_with_exact_mode": float((pe[:, 0] == pm[:, 0]).float().mean().item()),
                    "class_ranking_equal_exact_mode": bool(torch.equal(pe, pm))}
 
+    # the fp32-matching ("bit-exact") mode on the same workload, reported beside the headline mode
+    fp32_line = None
+    if world == 1 and mode == "bf16" and not args.no_fp32_line:
+        b200knn.set_default_mode("fp32")
+        for _ in range(2):
+            step_resident()
+        n_fp = max(2, min(5, args.steps))
+        fp_ms = timed(step_resident, n_fp) / n_fp
+        st = dict(K.last_rescore_stats)
+        ek = b200knn.topk_keys(q[:256].contiguous(), bank, KNN_K, mode="exact")
+        fk = b200knn.topk_keys(q[:256].contiguous(), bank, KNN_K, mode="fp32")
+        fp32_line = {"mode": "fp32", "dtype": "f16x2+f32", "value": Q / (fp_ms * 1e-3), "unit": "queries/s",
+                     "ms_per_step": fp_ms, "steps": n_fp, "uncertified_rows_last_step": st["uncertified"],
+                     "keys_bitwise_equal_exact_mode": bool(torch.equal(ek, fk)),
+                     "note": "tensor-core candidates (F16X2, 2 MMAs per k-step) + exact sequential-fma re-scoring + "
+                             "per-row certificate: neighbours, similarities and class ranking bit for bit those of "
+                             "the exact mode / oracle"}
+        b200knn.set_default_mode(mode)
+
     phases = None
     if world > 1:  # where a sharded step spends its time (one extra untimed step, rank 0's view)
         sb.phase_log = []
@@ -446,6 +469,8 @@ def main():
         }
         if quality is not None:
             line["quality"] = quality
+        if fp32_line is not None:
+            line["fp32_mode"] = fp32_line
         if phases is not None:
             line["config"]["phases_ms"] = phases
             line["config"]["exchange"] = "all-to-all of (B,k) keys by query slice + all-gather of (B,C) rankings (NCCL)"

@@ -117,11 +117,20 @@ def test_ties_duplicates_break_by_lowest_index():
 
 def test_merge_kernel_matches_oracle():
     rng = np.random.default_rng(0)
-    for (G, B, k_in, k_out) in [(2, 37, 200, 200), (8, 5, 200, 200), (3, 9, 20, 20), (5, 4, 10, 37), (37, 3, 200, 200)]:
+    # small batches with many lists run several warps per row (select.cu); ragged: lists cut short
+    # by a shared admission threshold (empty tails), as bank splits and shards return them
+    for (G, B, k_in, k_out, ragged) in [(2, 37, 200, 200, False), (8, 5, 200, 200, False), (3, 9, 20, 20, False),
+                                        (5, 4, 10, 37, False), (37, 3, 200, 200, False), (74, 64, 216, 216, True),
+                                        (16, 70, 16, 16, False), (9, 1300, 50, 50, True), (16, 6, 992, 992, True),
+                                        (52, 64, 16, 16, True)]:
         sims = rng.standard_normal((G, B, k_in)).astype(np.float32)
         sims[0, 0, :5] = 0.25
         idx = rng.permutation(G * B * k_in).reshape(G, B, k_in)
         keys = np.sort(O.make_keys(sims, idx), axis=2)[:, :, ::-1].copy()
+        if ragged:
+            keep = rng.integers(0, k_in + 1, size=(G, B))
+            keep[0] = k_in  # at least k_out keys survive in every row
+            keys[np.arange(k_in)[None, None, :] >= keep[:, :, None]] = 0
         got = b200knn.merge_keys(_t(keys.view(np.int64)), k_out).cpu().numpy().view(np.uint64)
         assert np.array_equal(got, O.merge_keys_np(keys, k_out))
 
