@@ -473,9 +473,10 @@ def main():
             line["fp32_mode"] = fp32_line
         if phases is not None:
             line["config"]["phases_ms"] = phases
-            line["config"]["exchange"] = "all-to-all of (B,k) keys by query slice + all-gather of (B,C) rankings (NCCL)"
+            line["config"]["exchange"] = "all-to-all of (B,k) keys by query slice (fused into the top-k kernel over NVLink peer memory when available) + all-gather of (B,C) rankings (NCCL)" + (
+                "; fp32: candidates routed to the shard owning each bank row for exact re-scoring and back (2 all-to-alls)" if mode in K.RESCORED_MODES else "")
         if mode in K.RESCORED_MODES:
-            line["config"]["uncertified_rows_last_step"] = rescore_stats["uncertified"]
+            line["config"]["uncertified_rows_last_step"] = rescore_stats["uncertified"] if world == 1 else sb.last_uncertified
         line["config"]["prepass"] = {"stride": K.prepass_stride(N, k_plan), "r": K.PREPASS["r"],
                                      "repaired_rows_last_step": prepass_stats["repaired"]}
         if world == 1 and not args.no_cpu_baseline:

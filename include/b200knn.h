@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200KNN_VERSION 110 /* 0.1.1: b200knn_rescore takes a workspace and the two extra certificate terms */
+#define B200KNN_VERSION 120 /* 0.1.2: + b200knn_route_keys, b200knn_certify (sharded fp32 mode); 0.1.1: b200knn_rescore workspace */
 
 /* error codes */
 #define B200KNN_OK 0
@@ -244,6 +244,25 @@ int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_
                     int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
                     void* stream);
 size_t b200knn_rescore_workspace_bytes(int64_t B, int k_in);
+
+/*
+ * Sharded fp32 mode (no counterpart in the reference, which is single-device): the owner of a
+ * query merges every shard's approximate candidates, has each candidate re-scored by the shard
+ * that holds its bank row, merges the exact keys that come back and certifies the result.
+ * b200knn_route_keys: out (n_shards, n, k): out[g][r][:] = the keys of row r whose bank row lies in
+ *   [g*rows_per_shard, (g+1)*rows_per_shard), in their original order, compacted to the front and
+ *   zero-padded — the send buffer of that exchange.  The shards re-score what they receive with
+ *   b200knn_rescore (k_out = k_in; empty slots, and whole empty 32-slot units, are skipped).
+ * b200knn_certify: the certificate of b200knn_rescore on its own: exact_keys (B,k) merged exact
+ *   keys, approx_keys (B,k_in) merged approximate candidates (both sorted descending);
+ *   all_rows != 0 when k_in covers the whole bank.
+ */
+int b200knn_route_keys(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int n_shards,
+                       uint64_t* out, void* stream);
+int b200knn_certify(const void* q, int q_dtype, int64_t q_ld, int dim, const uint64_t* exact_keys, int k,
+                    const uint64_t* approx_keys, int k_in, int64_t B, int all_rows, float err_coef,
+                    float err_abs, float max_abs, const float* bank_max_norm, int32_t* uncertified,
+                    int32_t* n_uncertified, void* stream);
 
 /*
  * SURVEY.md §8(f) rows — the steps either side of knn_predict in the reference.

@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# N-GPU check of the sharded fp32 mode (re-scoring at the row owner): unit tests of the new kernels, bitwise check, benches
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+G=${1:-2}
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+echo "== rescore tests"; timeout 600 python -m pytest tests/test_gpu_rescore.py -m gpu -x -q 2>&1 | tail -5
+echo "== sharded check"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 scripts/sharded_check.py 2>&1 | grep -E "rank 0|Error|error|Traceback|assert" | tail -20 | tee gpurun_out/sharded_check_g$G.log
+F='"value": [0-9.]*\|"ms_per_step": [0-9.]*\|"kernel_ms": [0-9.]*\|"phases_ms": {[^}]*}\|"uncertified_rows_last_step": [0-9]*'
+echo "== bench fp32 gpus=$G (re-score at row owner)"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $G --mode fp32 --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_fp32_g${G}.log | grep -o "$F"
+echo "== bench fp32 gpus=$G (re-score per shard, previous design)"
+B200KNN_SHARDED_RESCORE=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29516 bench.py --gpus $G --mode fp32 --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_fp32_g${G}_pershard.log | grep -o "$F"
+echo "== bench bf16 gpus=$G"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $G --mode bf16 --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_bf16_g${G}.log | grep -o "$F"

@@ -634,6 +634,87 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
     return out, flags, n_bad
 
 
+# ---- pieces of the sharded fp32 mode (b200knn/sharded.py): candidates are merged by the owner of
+# a query, re-scored by the shard that owns each candidate's bank row, merged again and certified
+def first_level(feature_bank: torch.Tensor, mode: str) -> dict:
+    """The candidate level a rescored mode starts with on this bank (LEVELS entry + its name)."""
+    name = _cascade_levels(feature_bank, mode)[0]
+    return dict(LEVELS[name], name=name)
+
+
+def route_keys(keys: torch.Tensor, rows_per_shard: int, n_shards: int) -> torch.Tensor:
+    """(n, k) keys -> (n_shards, n, k): block g keeps the keys whose bank row shard g owns."""
+    n, k = keys.shape
+    out = torch.empty((n_shards, n, k), dtype=torch.int64, device=keys.device)
+    if n:
+        keys = keys.contiguous()
+        with torch.cuda.device(keys.device):
+            _lib.check(_lib.load().b200knn_route_keys(keys.data_ptr(), n, k, rows_per_shard, n_shards,
+                                                      out.data_ptr(), _stream()), "route_keys")
+    return out
+
+
+def rescore_sparse(feature: torch.Tensor, feature_bank: torch.Tensor, cand: torch.Tensor, cand_mode: str,
+                   idx_offset: int) -> torch.Tensor:
+    """Exact (sequential-fma) keys of the candidates in `cand` (B, k_in; empty slots allowed anywhere;
+    indices offset by idx_offset into this bank), sorted descending, zero-padded: (B, k_in)."""
+    lib = _lib.load()
+    B, D = feature.shape
+    N = feature_bank.shape[1]
+    k_in = cand.shape[1]
+    dev = feature.device
+    pb = bank_cache.get(feature_bank, cand_mode)
+    rows_a, rows_b = pb.rescore_rows()
+    q = feature if feature.dtype == torch.float32 else feature.float()
+    if q.stride(1) != 1:
+        q = q.contiguous()
+    out = torch.empty((B, k_in), dtype=torch.int64, device=dev)
+    if B == 0:
+        return out
+    cand = cand.contiguous()
+    with torch.cuda.device(dev):
+        flags = torch.empty((B,), dtype=torch.int32, device=dev)
+        n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.b200knn_rescore_workspace_bytes(B, k_in)) if rows_b is None else 0
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+        _lib.check(lib.b200knn_rescore(q.data_ptr(), _DTYPES[q.dtype], q.stride(0), rows_a.data_ptr(),
+                                       _ptr(rows_b), N, D, cand.data_ptr(), B, k_in, k_in, idx_offset,
+                                       0.0, 0.0, 0.0, pb.max_norm().data_ptr(), out.data_ptr(),
+                                       flags.data_ptr(), n_bad.data_ptr(), _ptr(ws), ws_bytes, _stream()),
+                   "rescore")
+    return out
+
+
+def certify(exact: torch.Tensor, approx: torch.Tensor, feature: torch.Tensor, level: dict,
+            max_norm: torch.Tensor, all_rows: bool) -> torch.Tensor:
+    """(n,) int32 flags: 1 where the exact k-th key does not beat the approximate k_in-th by the
+    level's error bound (see b200knn_rescore)."""
+    n, k = exact.shape
+    k_in = approx.shape[1]
+    D = feature.shape[1]
+    dev = exact.device
+    flags = torch.zeros((n,), dtype=torch.int32, device=dev)
+    if n == 0:
+        return flags
+    q = feature if feature.dtype in _DTYPES else feature.float()
+    if q.stride(1) != 1:
+        q = q.contiguous()
+    exact, approx = exact.contiguous(), approx.contiguous()
+    with torch.cuda.device(dev):
+        n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().b200knn_certify(
+            q.data_ptr(), _DTYPES[q.dtype], q.stride(0), D, exact.data_ptr(), k, approx.data_ptr(), k_in, n,
+            1 if all_rows else 0, float(level["err_coef"]),
+            float(level.get("err_abs", 0.0)) * math.sqrt(padded_dim(D)), float(level.get("max_abs", 0.0)),
+            max_norm.data_ptr(), flags.data_ptr(), n_bad.data_ptr(), _stream()), "certify")
+    return flags
+
+
+def bank_max_norm(feature_bank: torch.Tensor, cand_mode: str) -> torch.Tensor:
+    """Device scalar: max row norm of this bank (x1.001), as the certificate uses it."""
+    return bank_cache.get(feature_bank, cand_mode).max_norm()
+
+
 def _cascade_levels(feature_bank: torch.Tensor, mode: str):
     levels = list(CASCADES[mode])
     if len(levels) > 1 and levels[0] == "fp32_f16x2" and padded_dim(feature_bank.shape[0]) > MAX_BF16_DIM:

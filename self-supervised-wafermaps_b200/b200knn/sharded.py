@@ -101,6 +101,32 @@ class _CudaOps:
         from .knn import decode_keys
         return decode_keys(keys)
 
+    # ---- sharded fp32 mode: candidate level, routing, re-scoring of routed candidates, certificate
+    @staticmethod
+    def first_level(bank_shard, mode):
+        from .knn import RESCORED_MODES, first_level
+        return first_level(bank_shard, mode) if mode in RESCORED_MODES else None
+
+    @staticmethod
+    def route_keys(keys, rows_per_shard, n_shards):
+        from .knn import route_keys
+        return route_keys(keys, rows_per_shard, n_shards)
+
+    @staticmethod
+    def rescore_sparse(feature, bank_shard, cand, cand_mode, idx_offset):
+        from .knn import rescore_sparse
+        return rescore_sparse(feature, bank_shard, cand, cand_mode, idx_offset)
+
+    @staticmethod
+    def certify(exact, approx, feature, level, max_norm, all_rows):
+        from .knn import certify
+        return certify(exact, approx, feature, level, max_norm, all_rows)
+
+    @staticmethod
+    def bank_max_norm(bank_shard, cand_mode):
+        from .knn import bank_max_norm
+        return bank_max_norm(bank_shard, cand_mode)
+
 
 class ShardedBank:
     """A (D, N) bank whose columns (bank rows) are partitioned over a process group.
@@ -197,6 +223,41 @@ class ShardedBank:
                 sub = feature[rows].contiguous()
                 merged[rows] = self.ops.merge_keys(self._gather(self.local_keys(sub, k, None)), k)
         return merged
+
+    def _knn_predict_rescored(self, feature, C, knn_k, knn_t, level) -> torch.Tensor:
+        B = feature.shape[0]
+        per, lo, hi = self._owned(B)
+        self._mark("start")
+        merged, flags = self._owned_keys_rescored(feature, knn_k, level)
+        packed = self.ops.vote_packed(merged[:hi - lo], self.labels, C, knn_t, per)
+        packed[:hi - lo, C] |= flags.to(torch.int64) << 3  # status bit 3: not certified
+        gathered = torch.empty((per * self.world_size, C + 1), dtype=torch.int64, device=feature.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        self._mark("vote+gather")
+        status = gathered[:B, C]
+        out = gathered[:B, :C].contiguous()
+        worst = int(status.max().item())  # the one host synchronisation of the call
+        redo = (status & 9) != 0          # starved (bit 0) or uncertified (bit 3) rows
+        # identical on every rank -> every rank takes the same branches (collectives stay matched)
+        if worst & 9:
+            rows = redo.nonzero(as_tuple=False).view(-1)
+            sub = feature[rows].contiguous()
+            # per-shard exact top-k through the single-GPU cascade, all-gathered and merged
+            keys = self.ops.merge_keys(self._gather(self.local_keys(sub, knn_k, None)), knn_k)
+            pk = self.ops.vote_packed(keys, self.labels, C, knn_t, rows.numel())
+            out[rows] = pk[:, :C]
+            worst = (worst & 6) | (int(pk[:, C].max().item()) & 6)
+            self.last_uncertified = int(rows.numel())
+        else:
+            self.last_uncertified = 0
+        if worst & 2:
+            raise RuntimeError("index out of bounds: a feature_labels entry is outside "
+                               f"[0, num_classes={C})")
+        if worst & 4:
+            raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
+        return out
+
+    last_uncertified = 0
 
     def knn_topk(self, feature: torch.Tensor, k: int):
         return self.ops.decode_keys(self.topk_keys(feature, k))
@@ -295,6 +356,55 @@ class ShardedBank:
         self._mark("  all-to-all")
         return self.ops.merge_keys(recv, k)
 
+    # ------------------------------------------------------------------ sharded fp32 (bit-exact) mode
+    rescore_at_row_owner = os.environ.get("B200KNN_SHARDED_RESCORE", "1") == "1"
+
+    def _global_max_norm(self, cand_mode: str) -> torch.Tensor:
+        """max row norm over the WHOLE bank (all-reduce MAX of the shards' values), cached."""
+        key = ("max_norm", cand_mode)
+        hit = self._symm.get(key)
+        if hit is None:
+            hit = self.ops.bank_max_norm(self.bank_shard, cand_mode).clone()
+            dist.all_reduce(hit, op=dist.ReduceOp.MAX, group=self.group)
+            self._symm[key] = hit
+        return hit
+
+    def _owned_keys_rescored(self, feature: torch.Tensor, k: int, level: dict):
+        """fp32-matching mode with the bank sharded, re-scoring work divided by the shard count:
+        1. every shard's tensor-core candidates (k + margin, under one global sampled threshold) go
+           to the owner of the query (fused scatter / all-to-all) and are merged there: the global
+           approximate top-(k + margin), exactly what one GPU would have produced;
+        2. the owner routes each candidate to the shard that holds its bank row (all-to-all), that
+           shard re-scores it exactly (sequential fma) and returns the exact key (all-to-all);
+        3. the owner merges the exact keys and evaluates the single-GPU certificate.
+        Returns (exact keys (per, k), uncertified flags (n_owned,) int32) for the owned query rows."""
+        import copy
+        B = feature.shape[0]
+        per, lo, hi = self._owned(B)
+        G = self.world_size
+        k_in = min(k + level["margin"], self.n_rows)
+        cand = copy.copy(self)  # same shard, buffers and phase log; candidate mode instead of "fp32"
+        cand.mode = level["cand"]
+        tau0 = cand.global_threshold(feature, k_in)
+        self._mark("threshold")
+        approx = cand.owned_keys(feature, k_in, tau0)                  # (per, k_in)
+        self._mark("candidates+exchange+merge")
+        rows_per_shard = (self.n_rows + G - 1) // G
+        routed = self.ops.route_keys(approx, rows_per_shard, G)       # (G, per, k_in)
+        mine = self._exchange_owned(routed.view(G * per, k_in), per)   # (G, per, k_in): all queries, my rows
+        self._mark("  route + all-to-all")
+        exact_local = torch.zeros((G * per, k_in), dtype=torch.int64, device=feature.device)
+        if B:
+            exact_local[:B] = self.ops.rescore_sparse(feature, self.bank_shard, mine.view(G * per, k_in)[:B],
+                                                      level["cand"], self.lo)
+        self._mark("  re-score")
+        back = self._exchange_owned(exact_local, per)                  # (G, per, k_in): my queries, every shard
+        merged = self.ops.merge_keys(back, k)                          # (per, k) exact
+        flags = self.ops.certify(merged[:hi - lo], approx[:hi - lo], feature[lo:hi], level,
+                                 self._global_max_norm(level["cand"]), k_in >= self.n_rows)
+        self._mark("  all-to-all + merge + certify")
+        return merged, flags
+
     def knn_predict(self, feature: torch.Tensor, num_classes: int, knn_k: int = 200,
                     knn_t: float = 0.1, exchange: str = "alltoall") -> torch.Tensor:
         """Same contract as ``knn_predict`` with the bank sharded; identical on every rank."""
@@ -304,6 +414,9 @@ class ShardedBank:
             raise ValueError(f"unknown exchange {exchange!r}")
         if knn_k > self.n_rows:
             raise RuntimeError("selected index k out of range")
+        level = self.ops.first_level(self.bank_shard, self.mode) if hasattr(self.ops, "first_level") else None
+        if level is not None and self.rescore_at_row_owner and feature.shape[0] > 0:
+            return self._knn_predict_rescored(feature, int(num_classes), knn_k, knn_t, level)
         B, C = feature.shape[0], int(num_classes)
         per, lo, hi = self._owned(B)
         mark = self._mark

@@ -312,6 +312,45 @@ int b200knn_rescore(const void* q, int q_dtype, int64_t q_ld, const float* rows_
   return e == cudaSuccess ? B200KNN_OK : fail_cuda("rescore", e);
 }
 
+int b200knn_certify(const void* q, int q_dtype, int64_t q_ld, int dim, const uint64_t* exact_keys, int k,
+                    const uint64_t* approx_keys, int k_in, int64_t B, int all_rows, float err_coef,
+                    float err_abs, float max_abs, const float* bank_max_norm, int32_t* uncertified,
+                    int32_t* n_uncertified, void* stream) {
+  if (!q || !exact_keys || !approx_keys || !bank_max_norm || !uncertified || !n_uncertified)
+    return fail(B200KNN_E_ARG, "certify: null pointer");
+  if (B < 0 || dim <= 0 || k <= 0 || k_in < k) return fail(B200KNN_E_ARG, "certify: bad shape (need 0 < k <= k_in)");
+  if (q_dtype < 0 || q_dtype > 2) return fail(B200KNN_E_ARG, "certify: unknown dtype");
+  b200knn::RescoreParams p = {};
+  p.q = q;
+  p.q_dtype = q_dtype;
+  p.q_ld = q_ld;
+  p.dim = dim;
+  p.dim_pad = (dim + 63) / 64 * 64;
+  p.cand = approx_keys;
+  p.B = B;
+  p.k_in = k_in;
+  p.k_out = k;
+  p.all_rows = all_rows ? 1 : 0;
+  p.err_coef = err_coef;
+  p.err_abs = err_abs;
+  p.max_abs = max_abs;
+  p.bank_max_norm = bank_max_norm;
+  p.out = const_cast<uint64_t*>(exact_keys);  // read only by the certificate kernel
+  p.uncertified = uncertified;
+  p.n_uncertified = n_uncertified;
+  cudaError_t e = b200knn::launch_certify(p, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("certify", e);
+}
+
+int b200knn_route_keys(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int n_shards,
+                       uint64_t* out, void* stream) {
+  if (!keys || !out || n < 0 || k <= 0 || rows_per_shard <= 0 || n_shards <= 0)
+    return fail(B200KNN_E_ARG, "route_keys: bad argument");
+  cudaError_t e = b200knn::launch_route_keys(keys, n, k, rows_per_shard, n_shards, out,
+                                             static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("route_keys", e);
+}
+
 size_t b200knn_rescore_workspace_bytes(int64_t B, int k_in) {
   if (B <= 0 || k_in <= 0) return 0;
   return b200knn::rescore_workspace_bytes(B, k_in);

@@ -73,6 +73,11 @@ struct RescoreParams {
 cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t workspace_bytes,
                            cudaStream_t stream);
 size_t rescore_workspace_bytes(int64_t B, int k_in);
+// the certificate alone: p.out = merged exact keys (read), p.cand = merged approximate candidates
+cudaError_t launch_certify(const RescoreParams& p, cudaStream_t stream);
+// split (n, k) key lists by owning shard: out (G, n, k), each shard's keys compacted to the front
+cudaError_t launch_route_keys(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int G,
+                              uint64_t* out, cudaStream_t stream);
 cudaError_t launch_row_norm_max(const float* a, const float* b, int64_t n, int dim_pad, float* out,
                                 cudaStream_t stream);
 

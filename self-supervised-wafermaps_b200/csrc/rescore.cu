@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(256)
       bulk_g2s(ptx::smem_u32(st.rows + lane * Stage::kPitch), p.rows_a + row * p.dim_pad + d0,
                uint32_t(len) * 4u, bar);
     const float* qrow = q32 + pb * p.q_ld;
-    if (q_vec16) {
+    if (valid == 0u) {
+      // an empty unit (routed lists of the sharded mode use ~1/G of their slots): no copies at all,
+      // the stage only goes through its barrier handshake and the consumer skips the fma chain
+    } else if (q_vec16) {
       for (int i = lane; i < len / 4; i += 32) {
         const int d = d0 + 4 * i;
         const int nb = max(0, min(16, (p.dim - d) * 4));
@@ -261,12 +264,14 @@ __global__ void __launch_bounds__(256)
   uint32_t phase = 0, klo = 0;
   int64_t cu = u_begin;
   float acc = 0.0f;
+  bool live = true;  // the unit holds at least one candidate
   for (int64_t t = 0; t < n_steps; ++t) {
     Stage& st = stages[cs];
     ptx::mbar_wait(ptx::smem_u32(&bars[cs]), phase, nullptr, 7);
     if (cc == 0) {
       acc = 0.0f;
       klo = st.klo[lane];
+      live = __any_sync(kFull, klo != 0u);
     }
     const int len4 = min(CHUNK, p.dim_pad - cc * CHUNK) / 4;
     const float4* xr = reinterpret_cast<const float4*>(st.rows + lane * Stage::kPitch);
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(256)
       w[i] = qr[i];
     }
 #pragma unroll 1
-    for (int j = 0; j < len4; j += 8) {
+    for (int j = 0; live && j < len4; j += 8) {
       float4 xn[8], wn[8];
       const int jn = (j + 8 < len4) ? j + 8 : j;
 #pragma unroll
@@ -347,6 +352,54 @@ __global__ void __launch_bounds__(128)
     const int ok = certified(p, kth, last, sqrtf(qq) * 1.001f);
     p.uncertified[b] = ok ? 0 : 1;
     if (!ok) atomicAdd(p.n_uncertified, 1);
+  }
+}
+
+// The certificate alone (sharded fp32 mode: the exact keys of a query come back from the shards
+// that own the candidate rows and are merged by the query's owner): p.out holds the merged exact
+// keys (B, k_out), p.cand the merged approximate candidates (B, k_in).  One warp per query.
+__global__ void __launch_bounds__(128) certify_kernel(RescoreParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = int64_t(blockIdx.x) * 4 + warp;
+  if (b >= p.B) return;
+  float qq = 0.0f;
+  for (int d = lane; d < p.dim; d += 32) {
+    const float v = ldq(p.q, p.q_dtype, b * p.q_ld + d);
+    qq = fmaf(v, v, qq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(kFull, qq, o);
+  if (lane == 0) {
+    const int ok = certified(p, p.out[b * p.k_out + p.k_out - 1], p.cand[b * p.k_in + p.k_in - 1],
+                             sqrtf(qq) * 1.001f);
+    p.uncertified[b] = ok ? 0 : 1;
+    if (!ok) atomicAdd(p.n_uncertified, 1);
+  }
+}
+
+// out[g][r][:] = the keys of row r whose bank row belongs to shard g (rows [g*rows_per_shard, ...)),
+// in their original order, compacted to the front and zero-padded: the query owner's candidate list
+// split by the shard that can re-score each candidate.  Compact lists let the re-scoring kernel
+// skip the empty 32-slot units (with G shards only ~1/G of the slots are used).  One warp per row.
+__global__ void __launch_bounds__(128)
+    route_keys_kernel(const uint64_t* __restrict__ keys, int64_t n, int k, int64_t rows_per_shard, int G,
+                      uint64_t* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = int64_t(blockIdx.x) * 4 + warp;
+  if (r >= n) return;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint64_t* row = keys + r * k;
+  for (int g = 0; g < G; ++g) {
+    uint64_t* o = out + (int64_t(g) * n + r) * k;
+    int cnt = 0;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const uint64_t key = j0 + lane < k ? row[j0 + lane] : 0ull;
+      const bool mine = key != 0 && key_idx(key) / rows_per_shard == g;
+      const unsigned bm = __ballot_sync(kFull, mine);
+      if (mine) o[cnt + __popc(bm & lt_mask)] = key;
+      cnt += __popc(bm);
+    }
+    for (int j = cnt + lane; j < k; j += 32) o[j] = 0ull;
   }
 }
 
@@ -449,6 +502,19 @@ cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t works
   if (items <= 16) return launch_rescore_t<16>(p, stream);
   if (items <= 32) return launch_rescore_t<32>(p, stream);
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_certify(const RescoreParams& p, cudaStream_t stream) {
+  if (p.B == 0) return cudaSuccess;
+  certify_kernel<<<unsigned((p.B + 3) / 4), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_route_keys(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int G,
+                              uint64_t* out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  route_keys_kernel<<<unsigned((n + 3) / 4), 128, 0, stream>>>(keys, n, k, rows_per_shard, G, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_row_norm_max(const float* a, const float* b, int64_t n, int dim_pad, float* out,

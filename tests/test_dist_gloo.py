@@ -22,9 +22,18 @@ class OracleOps:
     sample_r = 16
     poison_threshold = False  # force the (1e-7-probability) failure of the sampled bound
 
+    force_uncertified = False  # sharded fp32 mode: fail the certificate of every rank's first owned row
+
+    @staticmethod
+    def _sims(feature, bank_shard, mode):
+        q = feature.numpy()
+        if mode == "f16x2":  # the candidate pass: fp16-rounded queries (one-sided 2^-11 operand error)
+            q = q.astype(np.float16).astype(np.float32)
+        return O.sims_seqfma(q, bank_shard.numpy())
+
     @classmethod
     def topk_keys(cls, feature, bank_shard, k, mode, idx_offset, tau0=None):
-        sims = O.sims_seqfma(feature.numpy(), bank_shard.numpy())
+        sims = cls._sims(feature, bank_shard, mode)
         if tau0 is not None:
             sims = np.where(sims > tau0.numpy()[:, None], sims, -np.inf)
         s, i = O.canonical_topk_c(sims, k, idx_offset)
@@ -36,9 +45,9 @@ class OracleOps:
     def sample_keys(cls, feature, bank_shard, k, mode, n_rows_global):
         if cls.sample_stride == 0:
             return None
-        sub = bank_shard.numpy()[:, :: cls.sample_stride]
+        sub = bank_shard[:, :: cls.sample_stride].contiguous()
         r = min(cls.sample_r, sub.shape[1])
-        s, i = O.topk_seqfma(feature.numpy(), np.ascontiguousarray(sub), r)
+        s, i = O.canonical_topk_c(cls._sims(feature, sub, mode), r)
         return torch.from_numpy(O.make_keys(s, i).view(np.int64))
 
     @classmethod
@@ -72,6 +81,52 @@ class OracleOps:
         s, i = O.decode_keys(keys.numpy().view(np.uint64))
         return torch.from_numpy(s), torch.from_numpy(i)
 
+    # ---- sharded fp32 mode (same contract as _CudaOps)
+    @staticmethod
+    def first_level(bank_shard, mode):
+        from b200knn.knn import LEVELS
+        return dict(LEVELS["fp32_f16x2"], name="fp32_f16x2") if mode == "fp32" else None
+
+    @staticmethod
+    def route_keys(keys, rows_per_shard, n_shards):
+        kk = keys.numpy().view(np.uint64)
+        _, idx = O.decode_keys(kk)
+        out = np.zeros((n_shards,) + kk.shape, dtype=np.uint64)
+        for g in range(n_shards):
+            for r in range(kk.shape[0]):
+                mine = kk[r][(kk[r] != 0) & (idx[r] // rows_per_shard == g)]
+                out[g, r, :mine.size] = mine  # original order, compacted to the front
+        return torch.from_numpy(out.view(np.int64))
+
+    @staticmethod
+    def rescore_sparse(feature, bank_shard, cand, cand_mode, idx_offset):
+        kk = cand.numpy().view(np.uint64)
+        _, idx = O.decode_keys(kk)
+        sims = O.sims_seqfma(feature.numpy(), bank_shard.numpy())
+        out = np.zeros(kk.shape, dtype=np.uint64)
+        for b in range(kk.shape[0]):
+            cols = idx[b][kk[b] != 0]
+            keys = np.sort(O.make_keys(sims[b, cols - idx_offset][None], cols[None])[0])[::-1]
+            out[b, :keys.size] = keys
+        return torch.from_numpy(out.view(np.int64))
+
+    @classmethod
+    def certify(cls, exact, approx, feature, level, max_norm, all_rows):
+        es, _ = O.decode_keys(exact.numpy().view(np.uint64))
+        as_, _ = O.decode_keys(approx.numpy().view(np.uint64))
+        qn = np.linalg.norm(feature.numpy().astype(np.float64), axis=1) * 1.001
+        m = float(max_norm)
+        e = level["err_coef"] * qn * m + level.get("err_abs", 0.0) * np.sqrt(feature.shape[1]) * (qn + m)
+        ok = np.isfinite(es[:, -1]) & (es[:, -1] > as_[:, -1] + e)
+        ok = np.where(np.isneginf(as_[:, -1]), bool(all_rows), ok)
+        if cls.force_uncertified and ok.size:
+            ok[0] = False
+        return torch.from_numpy((~ok).astype(np.int32))
+
+    @staticmethod
+    def bank_max_norm(bank_shard, cand_mode):
+        return torch.tensor([float(np.linalg.norm(bank_shard.numpy(), axis=0).max()) * 1.001])
+
 
 def _free_port():
     with socket.socket() as s:
@@ -79,16 +134,17 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, out_dir, stride=0, poison=False):
+def _worker(rank, world, port, case, out_dir, stride=0, poison=False, mode="bf16", force_uncertified=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from b200knn import ShardedBank
 
         OracleOps.sample_stride, OracleOps.poison_threshold = stride, poison
+        OracleOps.force_uncertified = force_uncertified
         c = datagen.make_case(case)
         bank = torch.from_numpy(c["bank"])
-        sb = ShardedBank.from_full(bank, torch.from_numpy(c["labels"]), ops=OracleOps, mode="bf16")
+        sb = ShardedBank.from_full(bank, torch.from_numpy(c["labels"]), ops=OracleOps, mode=mode)
         q = torch.from_numpy(c["feature"])
         keys = sb.topk_keys(q, c["k"])
         pred = sb.knn_predict(q, c["C"], c["k"], c["t"])  # all-to-all by query slice (default)
@@ -96,6 +152,7 @@ def _worker(rank, world, port, case, out_dir, stride=0, poison=False):
         assert torch.equal(pred, pred_ag)
         np.save(os.path.join(out_dir, f"keys_{rank}.npy"), keys.numpy())
         np.save(os.path.join(out_dir, f"pred_{rank}.npy"), pred.numpy())
+        np.save(os.path.join(out_dir, f"redo_{rank}.npy"), np.array([sb.last_uncertified]))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -117,6 +174,31 @@ def test_sharded_equals_single(world, case, stride, poison, tmp_path):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"keys_{r}.npy"), want_keys)  # bitwise, every rank
         assert np.array_equal(np.load(tmp_path / f"pred_{r}.npy"), want_pred)
+
+
+@pytest.mark.parametrize("world,case,stride,poison,force", [
+    (2, "clustered_small", 0, False, False),  # no pre-pass: every shard sends its full candidate list
+    (3, "gauss_small", 4, False, False),      # global sampled threshold
+    (2, "mixed38", 4, False, True),           # one certificate per rank forced to fail -> cascade fallback
+    (3, "clustered_small", 4, True, False),   # a starved row (threshold too high) -> uncertified -> fallback
+    (2, "ragged", 0, False, False),           # B = 7 over 2 ranks, D = 72, k + margin > a shard's share of the top
+])
+def test_sharded_fp32_rescored_at_row_owner(world, case, stride, poison, force, tmp_path):
+    """The sharded fp32 mode: approximate candidates merged by the query's owner, each re-scored by
+    the shard that owns its bank row, exact keys merged and certified by the query's owner —
+    predictions bit for bit those of the sequential-fma oracle on every rank."""
+    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path), stride, poison, "fp32", force),
+             nprocs=world, join=True)
+    c = datagen.make_case(case)
+    s, i = O.topk_seqfma(c["feature"], c["bank"], c["k"])
+    want_pred = O.vote_o64(s, i, c["labels"], c["C"], c["t"])[0]
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"pred_{r}.npy"), want_pred)
+        assert np.array_equal(np.load(tmp_path / f"keys_{r}.npy"), O.make_keys(s, i).view(np.int64))
+        redo = int(np.load(tmp_path / f"redo_{r}.npy")[0])
+        # (the emulated pre-pass, 16 best of every 4th row, is tighter than the product's stride rule
+        # and starves some rows of their k + margin candidates: those legitimately take the fallback)
+        assert (redo >= world) if force else (redo >= 1 if poison else (redo == 0 or stride > 0))
 
 
 def test_shard_smaller_than_k(tmp_path):

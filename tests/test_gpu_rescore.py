@@ -37,8 +37,10 @@ def _rescore(q, rows_pad, cand, N, D, k_out, idx_offset, err_coef, max_norm, use
     (3, 400, 1, 33, 10, 0),           # D = 1
     (1, 50, 384, 50, 50, 0),          # every bank row is a candidate (k_in == N)
     (700, 20000, 64, 17, 5, 0),       # one chunk per unit, many units per warp
+    (60, 4000, 512, 240, 240, -1),    # routed lists of the sharded mode: 0..40 candidates, whole empty units
 ])
 def test_rescore_both_kernels_match_seqfma(B, N, D, k_in, k_out, q_pad):
+    sparse, q_pad = q_pad < 0, max(q_pad, 0)
     rng = np.random.default_rng(B * 7 + D)
     bank = rng.standard_normal((N, D)).astype(np.float32)
     qfull = rng.standard_normal((B, D + q_pad)).astype(np.float32)
@@ -59,6 +61,11 @@ def test_rescore_both_kernels_match_seqfma(B, N, D, k_in, k_out, q_pad):
     for b in range(0, B, 3):
         n_valid[b] = max(k_out, k_in - 1 - (b % 7)) if k_in > k_out else k_in
         cand[b, n_valid[b]:] = 0
+    if sparse:
+        n_valid = rng.integers(0, 41, size=B)
+        n_valid[:3] = 0
+        for b in range(B):
+            cand[b, n_valid[b]:] = 0
 
     sims = O.sims_seqfma(np.ascontiguousarray(q), np.ascontiguousarray(bank.T))  # (B, N) sequential fma
     want = np.zeros((B, k_out), dtype=np.uint64)
@@ -122,3 +129,37 @@ def test_rescore_certificate_terms():
     assert run(0.0, float(gap.max()) * 0.6, 0.0).all()   # err_abs * (1 + 1) above every gap
     assert run(0.0, 0.0, 0.5).all()                      # ||q|| = 1 >= max_abs
     assert not run(0.0, 0.0, 2.0).any()
+
+
+def test_route_keys_and_certify_match_numpy():
+    """The two small kernels of the sharded fp32 mode against their numpy statements."""
+    rng = np.random.default_rng(11)
+    n, k_in, k, G, rows_per_shard, D = 37, 48, 20, 3, 1000, 72
+    idx = rng.integers(0, G * rows_per_shard, size=(n, k_in))
+    sims = -np.sort(-rng.standard_normal((n, k_in)).astype(np.float32), axis=1)
+    keys = O.make_keys(sims, idx)
+    keys[::4, -5:] = 0  # ragged tails
+    out = K.route_keys(torch.from_numpy(keys.view(np.int64)).to(DEV), rows_per_shard, G).cpu().numpy().view(np.uint64)
+    for g in range(G):
+        want = np.zeros_like(keys)
+        for r in range(n):
+            mine = keys[r][(keys[r] != 0) & (idx[r] // rows_per_shard == g)]
+            want[r, :mine.size] = mine  # original order, compacted to the front
+        assert np.array_equal(out[g], want)
+
+    q = rng.standard_normal((n, D)).astype(np.float32)
+    exact = O.make_keys(sims[:, :k] + np.float32(0.01), idx[:, :k])
+    level = dict(err_coef=1e-3, err_abs=1e-6, max_abs=0.0)
+    m = 2.5
+    flags = K.certify(torch.from_numpy(exact.view(np.int64)).to(DEV), torch.from_numpy(keys.view(np.int64)).to(DEV),
+                      torch.from_numpy(q).to(DEV), level, torch.tensor([m], dtype=torch.float32, device=DEV),
+                      all_rows=False).cpu().numpy()
+    qn = np.linalg.norm(q.astype(np.float64), axis=1) * 1.001
+    e = level["err_coef"] * qn * m + level["err_abs"] * np.sqrt(K.padded_dim(D)) * (qn + m)
+    es, _ = O.decode_keys(exact)
+    as_, _ = O.decode_keys(keys)
+    margin = es[:, -1].astype(np.float64) - (as_[:, -1].astype(np.float64) + e)
+    want = np.where(keys[:, -1] == 0, 1, (margin <= 0).astype(np.int32))
+    decided = (keys[:, -1] == 0) | (np.abs(margin) > 1e-5)  # away from fp32 rounding of the bound
+    assert np.array_equal(flags[decided], want[decided])
+    assert flags[::4].all()  # empty k_in-th slot with k_in < N: never certified
