@@ -64,3 +64,11 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: compiles whatever is stale, builds the oracle's C restatement and
+    verifies the loaded library against include/b200knn.h."""
+    import __graft_entry__
+
+    __graft_entry__.build()
