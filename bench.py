@@ -379,12 +379,12 @@ def main():
         st = dict(K.last_rescore_stats)
         ek = b200knn.topk_keys(q[:256].contiguous(), bank, KNN_K, mode="exact")
         fk = b200knn.topk_keys(q[:256].contiguous(), bank, KNN_K, mode="fp32")
-        fp32_line = {"mode": "fp32", "dtype": "f16x2+f32", "value": Q / (fp_ms * 1e-3), "unit": "queries/s",
+        fp32_line = {"mode": "fp32", "dtype": "f16+f32", "value": Q / (fp_ms * 1e-3), "unit": "queries/s",
                      "ms_per_step": fp_ms, "steps": n_fp, "uncertified_rows_last_step": st["uncertified"],
                      "keys_bitwise_equal_exact_mode": bool(torch.equal(ek, fk)),
-                     "note": "tensor-core candidates (F16X2, 2 MMAs per k-step) + exact sequential-fma re-scoring + "
-                             "per-row certificate: neighbours, similarities and class ranking bit for bit those of "
-                             "the exact mode / oracle"}
+                     "note": "tensor-core candidates (fp16, 1 MMA per k-step; rows it cannot certify: fp16 x split-fp16, "
+                             "2 MMAs) + exact sequential-fma re-scoring + per-row certificate: neighbours, similarities "
+                             "and class ranking bit for bit those of the exact mode / oracle"}
         b200knn.set_default_mode(mode)
 
     phases = None
@@ -417,6 +417,13 @@ def main():
                     + (" + rescore_dot_kernel" if mode in K.RESCORED_MODES else ""),
                     "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json); frac counts the useful "
                                    "2*N*D flops per query, executed_frac the 3 MMAs actually issued", "kernel_ms": kern}
+        elif cand_mode == "f16":
+            roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["bf16"], "traffic": None,
+                    "kernel": "tc_topk_kernel<F16,256,cta_group::2> candidates (1 fp16 MMA per k-step)"
+                    + (" + rescore_dot_kernel" if mode in K.RESCORED_MODES else ""),
+                    "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json; fp16 runs at the bf16 rate)",
+                    "kernel_ms": kern}
         elif cand_mode == "f16x2":
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                     "frac": achieved / pk["bf16"], "executed_frac": 2 * achieved / pk["bf16"],
@@ -451,13 +458,13 @@ def main():
             "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "f16x2": "f16x2", "exact": "f32",
-                      "fp32": "f16x2+f32", "fp32_f16x2": "f16x2+f32", "fp32_bf16x3": "bf16x3+f32",
+            "dtype": {"bf16": "bf16", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "f16x2": "f16x2", "f16": "f16", "exact": "f32",
+                      "fp32": "f16+f32", "fp32_f16": "f16+f32", "fp32_f16x2": "f16x2+f32", "fp32_bf16x3": "bf16x3+f32",
                       "fp32_tf32": "tf32x3+f32", "fp32_bf16": "bf16+f32"}[mode], "data": "synthetic",
             "config": {"workload": f"knn_predict N={N} D={DIM} k={KNN_K} t={KNN_T} C={N_CLASSES}; "
                                    f"Q={Q} queries per step (clustered synthetic, WM-811K class priors)",
                        "mode": mode, "bank_sharding": f"row-sharded over {world} GPU(s)" if world > 1 else "none",
-                       "l2": "inputs larger than L2 (prepared bank %.0f MB)" % (n_local * DIM * {"bf16": 2, "bf16x3": 4, "f16x2": 4, "tf32x3": 8, "exact": 4}[cand_mode] / 1e6),
+                       "l2": "inputs larger than L2 (prepared bank %.0f MB)" % (n_local * DIM * {"bf16": 2, "f16": 2, "bf16x3": 4, "f16x2": 4, "tf32x3": 8, "exact": 4}[cand_mode] / 1e6),
                        "plan": plan, "bank_prepare_ms_excluded": prepare_ms},
             "roofline": roof,
             "e2e": {"value": Q / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200KNN_VERSION 120 /* 0.1.2: + b200knn_route_keys, b200knn_certify (sharded fp32 mode); 0.1.1: b200knn_rescore workspace */
+#define B200KNN_VERSION 130 /* 0.1.3: + B200KNN_MODE_F16; 0.1.2: + b200knn_route_keys, b200knn_certify (sharded fp32 mode); 0.1.1: b200knn_rescore workspace */
 
 /* error codes */
 #define B200KNN_OK 0
@@ -62,6 +62,9 @@ extern "C" {
                                k-step: one-sided operand error 2^-11 ||q|| ||x|| (+ 2^-25 per element below the
                                fp16 normal range); values beyond +-65504 saturate.  Candidate generator of the
                                "fp32" cascade (b200knn_rescore certifies with err_abs / max_abs). */
+#define B200KNN_MODE_F16 6 /* tcgen05 kind::f16, fp16 queries x fp16 bank (one array each, the BF16 kernel on fp16
+                             data): two-sided operand error 2^-10 ||q|| ||x||, 8x tighter than BF16 at the same speed;
+                             same range rules as F16X2.  First level of the "fp32" cascade. */
 
 int b200knn_version(void);
 const char* b200knn_last_error(void);

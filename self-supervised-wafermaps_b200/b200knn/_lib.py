@@ -17,9 +17,9 @@ _DEFAULT = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb200knn.so"))
 # mirrors of the #defines in include/b200knn.h
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_DN, LAYOUT_ND = 0, 1
-MODE_EXACT, MODE_BF16, MODE_TF32X3, MODE_F32ROWS, MODE_BF16X3, MODE_F16X2 = 0, 1, 2, 3, 4, 5
+MODE_EXACT, MODE_BF16, MODE_TF32X3, MODE_F32ROWS, MODE_BF16X3, MODE_F16X2, MODE_F16 = 0, 1, 2, 3, 4, 5, 6
 SAMPLE_R = 16  # B200KNN_SAMPLE_R
-MODES = {"exact": MODE_EXACT, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3, "bf16x3": MODE_BF16X3, "f16x2": MODE_F16X2}
+MODES = {"exact": MODE_EXACT, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3, "bf16x3": MODE_BF16X3, "f16x2": MODE_F16X2, "f16": MODE_F16}
 
 # every symbol include/b200knn.h declares: (restype, argtypes)
 SIGNATURES = {

@@ -32,7 +32,7 @@ from . import _lib
 
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
-TC_MODES = ("bf16", "tf32x3", "bf16x3", "f16x2")  # raw tensor-core similarity modes
+TC_MODES = ("bf16", "tf32x3", "bf16x3", "f16x2", "f16")  # raw tensor-core similarity modes
 MAX_K = 992  # largest k of the streaming candidate lists (capacity 1024, include/b200knn.h)
 MAX_BF16_DIM = 768  # widest (padded) vector whose query tile the BF16 kernel can keep resident
 
@@ -64,7 +64,12 @@ profile_events = None
 #           2e-5 is the same empirical accumulation allowance as above.  Operands at or beyond
 #           fp16's range (max_abs) are refused.  The one-sided 2^-11 needs k+40 candidates where the
 #           split modes need k+16, and buys a third fewer MMAs than bf16x3 on CTA pairs.
+#   f16   : fp16 x fp16, one MMA per k-step (the BF16 kernel's speed).  Both operands are rounded:
+#           |error| <= 2^-10 (1 + 2^-12) ||q|| ||x|| + 2^-25 sqrt(D) (||q|| + ||x||); with k+40
+#           candidates ~99 % of the rows of the 811k x 512 workload certify, the rest goes to f16x2.
 LEVELS = {
+    "fp32_f16": dict(cand="f16", margin=40, err_coef=1.001 * 2.0 ** -10 + 2e-5,
+                     err_abs=1.01 * 2.0 ** -25, max_abs=6.0e4),
     "fp32_f16x2": dict(cand="f16x2", margin=40, err_coef=1.001 * (2.0 ** -11 + 2.0 ** -22) + 2e-5,
                        err_abs=1.01 * 2.0 ** -25, max_abs=6.0e4),
     "fp32_bf16": dict(cand="bf16", margin=128, err_coef=1.02 * 2.0 ** -7),
@@ -73,7 +78,8 @@ LEVELS = {
 }
 # mode -> levels tried in order (then "exact").  "fp32" skips its BF16 level for a bank on which
 # that level recently left more than CASCADE_GIVE_UP of the rows uncertified.
-CASCADES = {"fp32": ("fp32_f16x2", "fp32_bf16x3", "fp32_tf32"), "fp32_f16x2": ("fp32_f16x2",),
+CASCADES = {"fp32": ("fp32_f16", "fp32_f16x2", "fp32_bf16x3", "fp32_tf32"), "fp32_f16": ("fp32_f16",),
+            "fp32_f16x2": ("fp32_f16x2",),
             "fp32_bf16x3": ("fp32_bf16x3",),
             "fp32_bf16": ("fp32_bf16",), "fp32_tf32": ("fp32_tf32",)}
 CASCADE_GIVE_UP = 0.25
@@ -90,11 +96,13 @@ def set_default_mode(mode: str) -> None:
     """Select the similarity mode ``knn_predict``/``knn_topk`` use when none is passed.
 
     ``"exact"``     fp32 CUDA-core contraction, sequential-fma similarities (bitwise reproducible);
-    ``"fp32"``      tensor-core candidates + exact re-scoring + certificate, cascading fp16 x split-fp16
-                    (2 MMAs, k+40 candidates) -> split-BF16 (3 MMAs, k+16) -> 3xTF32 (k+8) -> exact for
-                    the rows each level cannot certify: bitwise the ``"exact"`` result at tensor-core
-                    speed (the fp32-matching mode);
-    ``"fp32_f16x2"`` / ``"fp32_bf16x3"`` / ``"fp32_tf32"`` / ``"fp32_bf16"``  a single level (then exact);
+    ``"fp32"``      tensor-core candidates + exact re-scoring + certificate, cascading fp16 (1 MMA per
+                    k-step, k+40 candidates) -> fp16 x split-fp16 (2 MMAs, k+40) -> split-BF16 (3 MMAs,
+                    k+16) -> 3xTF32 (k+8) -> exact for the rows each level cannot certify: bitwise the
+                    ``"exact"`` result at tensor-core speed (the fp32-matching mode);
+    ``"fp32_f16"`` / ``"fp32_f16x2"`` / ``"fp32_bf16x3"`` / ``"fp32_tf32"`` / ``"fp32_bf16"``  a single level
+                    (then exact);
+    ``"f16"``       raw tcgen05 fp16 similarities (2^-10 relative to ||q|| ||x||; BF16 mode's speed);
     ``"f16x2"``     raw tcgen05 fp16 x (fp16 hi + lo) similarities (~2.5e-4 relative to ||q|| ||x||);
     ``"bf16x3"``    raw tcgen05 bf16 hi/lo-split similarities (~1e-5 relative);
     ``"tf32x3"``    raw tcgen05 hi/lo-split TF32 similarities (fp32-class accuracy, ~1e-6);
@@ -139,16 +147,19 @@ def padded_dim(dim: int) -> int:
 class PreparedRows:
     """K-major rows in the layout the tensor-core kernel streams with TMA."""
 
-    __slots__ = ("mode", "n", "dim", "hi", "lo", "_f32", "_max_norm", "_src")
+    __slots__ = ("mode", "n", "dim", "hi", "lo", "_f32", "_max_norm", "_src", "_delegate")
 
     def __init__(self, mode: str, n: int, dim: int, hi: torch.Tensor, lo: Optional[torch.Tensor]):
         self.mode, self.n, self.dim, self.hi, self.lo = mode, n, dim, hi, lo
         self._f32 = None       # (n, dim_pad) fp32 shadow rows for the exact re-scoring (bf16 candidates)
         self._max_norm = None  # device scalar: max row norm (certificate)
         self._src = None       # (tensor, vectors_are_columns) to build the shadow lazily
+        self._delegate = None  # another preparation of the same bank that owns the shadow rows / norm
 
     def rescore_rows(self):
         """(rows_a, rows_b) fp32 row-major operands whose sum is the caller's exact value."""
+        if self._delegate is not None:
+            return self._delegate.rescore_rows()
         if self.mode == "tf32x3":  # hi + lo is exactly the caller's fp32 value
             return self.hi, self.lo
         if self._f32 is None:
@@ -160,6 +171,8 @@ class PreparedRows:
         return self._f32, None
 
     def max_norm(self) -> torch.Tensor:
+        if self._delegate is not None:
+            return self._delegate.max_norm()
         if self._max_norm is None:
             a, b = self.rescore_rows()
             out = torch.zeros((1,), dtype=torch.float32, device=a.device)
@@ -250,6 +263,9 @@ def prepare_rows(x: torch.Tensor, mode: str, vectors_are_columns: bool) -> Prepa
     elif mode == "bf16x3":
         hi = torch.empty((n, dpad), dtype=torch.bfloat16, device=x.device)
         lo = torch.empty((n, dpad), dtype=torch.bfloat16, device=x.device)
+    elif mode == "f16":
+        hi = torch.empty((n, dpad), dtype=torch.float16, device=x.device)
+        lo = None
     elif mode == "f16x2":  # queries: one fp16 array; bank: hi + lo
         hi = torch.empty((n, dpad), dtype=torch.float16, device=x.device)
         lo = torch.empty((n, dpad), dtype=torch.float16, device=x.device) if vectors_are_columns else None
@@ -275,7 +291,7 @@ class _BankCache:
     """Prepared banks keyed on the identity *and version* of the caller's tensor, so an
     in-place update or a rebuilt bank (new validation epoch) is re-prepared."""
 
-    def __init__(self, capacity: int = 4):
+    def __init__(self, capacity: int = 6):
         self.capacity = capacity
         self._entries = {}
         self._state = {}
@@ -286,7 +302,13 @@ class _BankCache:
         hit = self._entries.get(key)
         if hit is not None and hit[0]() is not None:
             return hit[1]
-        prep = prepare_rows(bank, mode, vectors_are_columns=True)
+        if mode == "f16":
+            # fp16(x) is the hi array of the f16x2 split (the next cascade level): share it
+            both = self.get(bank, "f16x2")
+            prep = PreparedRows("f16", both.n, both.dim, both.hi, None)
+            prep._src, prep._delegate = both._src, both
+        else:
+            prep = prepare_rows(bank, mode, vectors_are_columns=True)
         if len(self._entries) >= self.capacity:
             self._entries.pop(next(iter(self._entries)))
         try:
@@ -475,7 +497,7 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
         raise ValueError(f"unknown mode {mode!r}")
     _check_feature_bank(feature, feature_bank)
     B, D = feature.shape
-    if mode in ("bf16", "f16x2") and padded_dim(D) > MAX_BF16_DIM:
+    if mode in ("bf16", "f16x2", "f16") and padded_dim(D) > MAX_BF16_DIM:
         # these kernels keep a 128-row query tile resident in shared memory (D_pad * 256 B);
         # wider vectors go through the split kernel, which streams both operands
         mode = "bf16x3"
@@ -636,10 +658,9 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
 
 # ---- pieces of the sharded fp32 mode (b200knn/sharded.py): candidates are merged by the owner of
 # a query, re-scored by the shard that owns each candidate's bank row, merged again and certified
-def first_level(feature_bank: torch.Tensor, mode: str) -> dict:
-    """The candidate level a rescored mode starts with on this bank (LEVELS entry + its name)."""
-    name = _cascade_levels(feature_bank, mode)[0]
-    return dict(LEVELS[name], name=name)
+def cascade_levels(feature_bank: torch.Tensor, mode: str) -> list:
+    """The candidate levels a rescored mode tries in order on this bank (LEVELS entries + names)."""
+    return [dict(LEVELS[name], name=name) for name in _cascade_levels(feature_bank, mode)]
 
 
 def route_keys(keys: torch.Tensor, rows_per_shard: int, n_shards: int) -> torch.Tensor:
@@ -717,8 +738,9 @@ def bank_max_norm(feature_bank: torch.Tensor, cand_mode: str) -> torch.Tensor:
 
 def _cascade_levels(feature_bank: torch.Tensor, mode: str):
     levels = list(CASCADES[mode])
-    if len(levels) > 1 and levels[0] == "fp32_f16x2" and padded_dim(feature_bank.shape[0]) > MAX_BF16_DIM:
-        levels = levels[1:]  # no resident query tile at this width: start at the split-BF16 level
+    if len(levels) > 1 and padded_dim(feature_bank.shape[0]) > MAX_BF16_DIM:
+        # no resident query tile at this width: start at the split-BF16 level
+        levels = [lv for lv in levels if LEVELS[lv]["cand"] not in ("f16", "f16x2")]
     if len(levels) > 1:
         st = bank_cache.state(feature_bank)
         if st.get("skip_first", 0) > 0:

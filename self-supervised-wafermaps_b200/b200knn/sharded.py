@@ -28,7 +28,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-_TC_MODES = ("bf16", "tf32x3", "bf16x3", "f16x2")  # = knn.TC_MODES (raw tensor-core similarity modes)
+_TC_MODES = ("bf16", "tf32x3", "bf16x3", "f16x2", "f16")  # = knn.TC_MODES (raw tensor-core similarity modes)
 
 
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -103,9 +103,9 @@ class _CudaOps:
 
     # ---- sharded fp32 mode: candidate level, routing, re-scoring of routed candidates, certificate
     @staticmethod
-    def first_level(bank_shard, mode):
-        from .knn import RESCORED_MODES, first_level
-        return first_level(bank_shard, mode) if mode in RESCORED_MODES else None
+    def cascade_levels(bank_shard, mode):
+        from .knn import RESCORED_MODES, cascade_levels
+        return cascade_levels(bank_shard, mode) if mode in RESCORED_MODES else None
 
     @staticmethod
     def route_keys(keys, rows_per_shard, n_shards):
@@ -224,32 +224,46 @@ class ShardedBank:
                 merged[rows] = self.ops.merge_keys(self._gather(self.local_keys(sub, k, None)), k)
         return merged
 
-    def _knn_predict_rescored(self, feature, C, knn_k, knn_t, level) -> torch.Tensor:
-        B = feature.shape[0]
-        per, lo, hi = self._owned(B)
-        self._mark("start")
+    def _predict_level(self, feature, C, knn_k, knn_t, level):
+        """One cascade level for the given (replicated) query rows: ((n, C) rankings, (n,) status)
+        identical on every rank.  Status bits: 0 starved, 1 / 2 label / index out of range, 3 uncertified."""
+        n = feature.shape[0]
+        per, lo, hi = self._owned(n)
         merged, flags = self._owned_keys_rescored(feature, knn_k, level)
         packed = self.ops.vote_packed(merged[:hi - lo], self.labels, C, knn_t, per)
-        packed[:hi - lo, C] |= flags.to(torch.int64) << 3  # status bit 3: not certified
+        packed[:hi - lo, C] |= flags.to(torch.int64) << 3
         gathered = torch.empty((per * self.world_size, C + 1), dtype=torch.int64, device=feature.device)
         dist.all_gather_into_tensor(gathered, packed, group=self.group)
         self._mark("vote+gather")
-        status = gathered[:B, C]
-        out = gathered[:B, :C].contiguous()
-        worst = int(status.max().item())  # the one host synchronisation of the call
-        redo = (status & 9) != 0          # starved (bit 0) or uncertified (bit 3) rows
-        # identical on every rank -> every rank takes the same branches (collectives stay matched)
+        return gathered[:n, :C].contiguous(), gathered[:n, C].contiguous()
+
+    def _knn_predict_rescored(self, feature, C, knn_k, knn_t, levels) -> torch.Tensor:
+        self._mark("start")
+        out, status = self._predict_level(feature, C, knn_k, knn_t, levels[0])
+        worst = int(status.max().item())  # the one host synchronisation of a fully certified call
+        self.last_uncertified = 0
+        # Rows a level could not certify (or a sampled threshold starved) go to the next level; the
+        # status words are identical on every rank, so every rank takes the same branches and the
+        # collectives stay matched.
+        for level in levels[1:2]:
+            if not worst & 9:
+                break
+            rows = ((status & 9) != 0).nonzero(as_tuple=False).view(-1)
+            self.last_uncertified = max(self.last_uncertified, int(rows.numel()))
+            o2, s2 = self._predict_level(feature[rows].contiguous(), C, knn_k, knn_t, level)
+            out[rows] = o2
+            status[rows] = s2
+            worst = int(status.max().item())
         if worst & 9:
-            rows = redo.nonzero(as_tuple=False).view(-1)
+            rows = ((status & 9) != 0).nonzero(as_tuple=False).view(-1)
+            self.last_uncertified = max(self.last_uncertified, int(rows.numel()))
             sub = feature[rows].contiguous()
             # per-shard exact top-k through the single-GPU cascade, all-gathered and merged
             keys = self.ops.merge_keys(self._gather(self.local_keys(sub, knn_k, None)), knn_k)
             pk = self.ops.vote_packed(keys, self.labels, C, knn_t, rows.numel())
             out[rows] = pk[:, :C]
-            worst = (worst & 6) | (int(pk[:, C].max().item()) & 6)
-            self.last_uncertified = int(rows.numel())
-        else:
-            self.last_uncertified = 0
+            status[rows] = pk[:, C]
+            worst = int(status.max().item())
         if worst & 2:
             raise RuntimeError("index out of bounds: a feature_labels entry is outside "
                                f"[0, num_classes={C})")
@@ -414,9 +428,9 @@ class ShardedBank:
             raise ValueError(f"unknown exchange {exchange!r}")
         if knn_k > self.n_rows:
             raise RuntimeError("selected index k out of range")
-        level = self.ops.first_level(self.bank_shard, self.mode) if hasattr(self.ops, "first_level") else None
-        if level is not None and self.rescore_at_row_owner and feature.shape[0] > 0:
-            return self._knn_predict_rescored(feature, int(num_classes), knn_k, knn_t, level)
+        levels = self.ops.cascade_levels(self.bank_shard, self.mode) if hasattr(self.ops, "cascade_levels") else None
+        if levels and self.rescore_at_row_owner and feature.shape[0] > 0:
+            return self._knn_predict_rescored(feature, int(num_classes), knn_k, knn_t, levels)
         B, C = feature.shape[0], int(num_classes)
         per, lo, hi = self._owned(B)
         mark = self._mark

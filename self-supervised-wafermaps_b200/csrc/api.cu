@@ -31,7 +31,7 @@ int sm_count() {
 
 bool is_tc_mode(int mode) {
   return mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_TF32X3 || mode == B200KNN_MODE_BF16X3 ||
-         mode == B200KNN_MODE_F16X2;
+         mode == B200KNN_MODE_F16X2 || mode == B200KNN_MODE_F16;
 }
 
 bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan* plan) {
@@ -71,8 +71,8 @@ int b200knn_prepare_rows(const void* src, int src_dtype, int src_layout, int64_t
   if (src_layout != B200KNN_LAYOUT_DN && src_layout != B200KNN_LAYOUT_ND)
     return fail(B200KNN_E_ARG, "prepare_rows: unknown layout");
   if (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_TF32X3 && mode != B200KNN_MODE_F32ROWS &&
-      mode != B200KNN_MODE_BF16X3 && mode != B200KNN_MODE_F16X2)
-    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16, TF32X3, BF16X3, F16X2 or F32ROWS");
+      mode != B200KNN_MODE_BF16X3 && mode != B200KNN_MODE_F16X2 && mode != B200KNN_MODE_F16)
+    return fail(B200KNN_E_ARG, "prepare_rows: mode must be BF16, F16, TF32X3, BF16X3, F16X2 or F32ROWS");
   if ((mode == B200KNN_MODE_TF32X3 || mode == B200KNN_MODE_BF16X3) && !dst_lo)
     return fail(B200KNN_E_ARG, "prepare_rows: split modes need dst_lo");
   cudaError_t e = b200knn::launch_prepare(src, src_dtype, src_layout, n_vec, dim, ld, mode, dst_hi,
@@ -143,7 +143,8 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     e = b200knn::launch_exact(p, plan.grid, plan.cap, st);
     if (e != cudaSuccess) return fail_cuda("topk(exact)", e);
   } else if (is_tc_mode(mode)) {
-    if (mode == B200KNN_MODE_F16X2 ? !bank_lo : (mode != B200KNN_MODE_BF16 && (!q_lo || !bank_lo)))
+    if (mode == B200KNN_MODE_F16X2 ? !bank_lo
+                                   : (mode != B200KNN_MODE_BF16 && mode != B200KNN_MODE_F16 && (!q_lo || !bank_lo)))
       return fail(B200KNN_E_ARG, "topk: split modes need the lo operands");
     b200knn::TcParams p;
     p.mode = mode;

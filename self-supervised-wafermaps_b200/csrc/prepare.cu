@@ -10,6 +10,7 @@
 //   MODE_BF16  : dst_hi (n_vec, dim_pad) bf16, round-to-nearest-even
 //   MODE_TF32X3: dst_hi (n_vec, dim_pad) f32 = rna_tf32(x); dst_lo = x - hi
 //   MODE_BF16X3: dst_hi (n_vec, dim_pad) bf16 = rn(x); dst_lo = rn(x - hi)
+//   MODE_F16   : dst_hi only, as MODE_F16X2's
 //   MODE_F16X2 : dst_hi (n_vec, dim_pad) fp16 = rn(sat(x)); dst_lo (optional: bank only) = rn(sat(x - hi));
 //                sat clamps to +-65504 so that no inf/NaN ever enters the contraction
 //   MODE_F32ROWS: dst_hi (n_vec, dim_pad) f32 = x  (row-major shadow the exact re-scoring gathers)
@@ -40,7 +41,7 @@ __device__ __forceinline__ void emit(int mode, float x, void* hi, void* lo, int6
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     static_cast<__nv_bfloat16*>(hi)[o] = h;
     static_cast<__nv_bfloat16*>(lo)[o] = __float2bfloat16_rn(x - __bfloat162float(h));
-  } else if (mode == B200KNN_MODE_F16X2) {
+  } else if (mode == B200KNN_MODE_F16X2 || mode == B200KNN_MODE_F16) {
     const float sx = fminf(fmaxf(x, -65504.0f), 65504.0f);
     const __half h = __float2half_rn(sx);
     static_cast<__half*>(hi)[o] = h;

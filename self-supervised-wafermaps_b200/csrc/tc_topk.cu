@@ -31,6 +31,8 @@
 //              as CTA pairs like BF16: two MMAs per k-step instead of BF16X3's three, one-sided
 //              operand error 2^-11 (the query rounding) — candidate generator of the default
 //              "fp32" cascade.
+// MODE_F16   : the BF16 kernel on fp16 operands (one array each): two-sided operand error 2^-10,
+//              8x smaller than bf16's 2^-7 at the same speed — first level of the "fp32" cascade.
 // MODE_TF32X3: operands fp32 hi/lo split (prepare.cu), kind::tf32, UMMA
 //              128 x BLOCK_N x 8; per k-step  hi*lo + lo*hi + hi*hi  accumulate
 //              into the same TMEM tile; A and B are both streamed per k-block.
@@ -48,7 +50,8 @@
 namespace b200knn {
 
 int tc_tile_n(int mode, int dim) {
-  if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16X2) return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
+  if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16X2 || mode == B200KNN_MODE_F16)
+    return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
   return 128;
 }
 
@@ -59,7 +62,8 @@ bool tc_use_pair(int mode) {
     const char* e = getenv("B200KNN_NO_PAIR");
     no_pair = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  return (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16X2) && no_pair == 0;
+  if (mode == B200KNN_MODE_F16X2 || mode == B200KNN_MODE_F16) return true;  // pair-only instantiations
+  return mode == B200KNN_MODE_BF16 && no_pair == 0;
 }
 
 namespace {
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                    const __grid_constant__ CUtensorMap map_b_hi,
                    const __grid_constant__ CUtensorMap map_b_lo, const TcKernelArgs a) {
   // query tile resident in smem, only bank tiles are streamed (BF16, F16X2)
-  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16 || MODE == B200KNN_MODE_F16X2);
+  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16 || MODE == B200KNN_MODE_F16X2 || MODE == B200KNN_MODE_F16);
   constexpr int kBArrays = (MODE == B200KNN_MODE_F16X2) ? 2 : 1;  // bank arrays streamed per k-block (lo, hi)
   constexpr bool kHalf = (MODE != B200KNN_MODE_TF32X3);   // 2-byte elements (kind::f16)
   static_assert(!PAIR || kBf16, "CTA pairs are implemented for the resident-query modes");
@@ -146,7 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kElemsPerRow = kHalf ? 64 : 32;  // elements of one 128-byte k-block row
   constexpr int kUmmaKBytes = 32;                // one MMA consumes 32 bytes of k per row
   constexpr uint32_t kIdesc =
-      ptx::make_idesc(MODE == B200KNN_MODE_F16X2 ? 0u : (kHalf ? 1u : 2u), kTileM * kCtas, BLOCK_N);
+      ptx::make_idesc((MODE == B200KNN_MODE_F16X2 || MODE == B200KNN_MODE_F16) ? 0u : (kHalf ? 1u : 2u),
+                      kTileM * kCtas, BLOCK_N);
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -554,8 +559,10 @@ bool make_map(CUtensorMap* m, const void* base, bool bf16, uint64_t rows, uint64
 template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG, bool PAIR, bool SAMPLE = false>
 cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* dump, int32_t* diag,
                      int flags, const char** why) {
-  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16 || MODE == B200KNN_MODE_F16X2);  // resident query tile
-  constexpr bool kF16 = (MODE == B200KNN_MODE_F16X2);
+  constexpr bool kBf16 = (MODE == B200KNN_MODE_BF16 || MODE == B200KNN_MODE_F16X2 ||
+                          MODE == B200KNN_MODE_F16);  // resident query tile
+  constexpr bool kF16 = (MODE == B200KNN_MODE_F16X2 || MODE == B200KNN_MODE_F16);  // fp16 tensor maps
+  constexpr bool kTwoB = (MODE == B200KNN_MODE_F16X2);
   constexpr bool kHalf = (MODE != B200KNN_MODE_TF32X3);
   constexpr int kCtas = PAIR ? 2 : 1;
   constexpr int kBRows = BLOCK_N / kCtas;
@@ -597,14 +604,14 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   bool ok = make_map(&mq_hi, p.q_hi, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM, 1, kF16) &&
             make_map(&mb_hi, p.bank_hi, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride), kF16);
   if (ok && !kBf16) ok = make_map(&mq_lo, p.q_lo, kHalf, uint64_t(p.B), uint64_t(d_pad), kTileM);
-  if (ok && (!kBf16 || kF16))
+  if (ok && (!kBf16 || kTwoB))
     ok = make_map(&mb_lo, p.bank_lo, kHalf, uint64_t(p.N), uint64_t(d_pad), kBRows, uint64_t(p.bank_row_stride), kF16);
   if (!ok) {
     *why = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
   if (kBf16) mq_lo = mq_hi;
-  if (kBf16 && !kF16) mb_lo = mb_hi;
+  if (kBf16 && !kTwoB) mb_lo = mb_hi;
   auto kern = tc_topk_kernel<MODE, BLOCK_N, ITEMS, DEBUG, PAIR, SAMPLE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
@@ -656,14 +663,15 @@ cudaError_t launch_mode(const TcParams& p, int grid, int cap, cudaStream_t strea
     if (wide) return launch_cap<B200KNN_MODE_BF16, 256, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
     return launch_cap<B200KNN_MODE_BF16, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
   }
-  if (p.mode == B200KNN_MODE_F16X2) {
-    const bool wide = tc_tile_n(p.mode, p.D) == 256;
-    if (tc_use_pair(p.mode)) {
-      if (wide) return launch_cap<B200KNN_MODE_F16X2, 256, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
-      return launch_cap<B200KNN_MODE_F16X2, 128, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
-    }
-    if (wide) return launch_cap<B200KNN_MODE_F16X2, 256, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
-    return launch_cap<B200KNN_MODE_F16X2, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);
+  if (p.mode == B200KNN_MODE_F16X2) {  // CTA pairs only
+    if (tc_tile_n(p.mode, p.D) == 256)
+      return launch_cap<B200KNN_MODE_F16X2, 256, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
+    return launch_cap<B200KNN_MODE_F16X2, 128, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
+  }
+  if (p.mode == B200KNN_MODE_F16) {  // CTA pairs only
+    if (tc_tile_n(p.mode, p.D) == 256)
+      return launch_cap<B200KNN_MODE_F16, 256, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
+    return launch_cap<B200KNN_MODE_F16, 128, DEBUG, true>(p, grid, cap, stream, dump, diag, flags, why);
   }
   if (p.mode == B200KNN_MODE_TF32X3)
     return launch_cap<B200KNN_MODE_TF32X3, 128, DEBUG, false>(p, grid, cap, stream, dump, diag, flags, why);

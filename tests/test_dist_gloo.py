@@ -22,14 +22,17 @@ class OracleOps:
     sample_r = 16
     poison_threshold = False  # force the (1e-7-probability) failure of the sampled bound
 
-    force_uncertified = False  # sharded fp32 mode: fail the certificate of every rank's first owned row
+    force_uncertified = False  # sharded fp32 mode: fail the certificate of every rank's first owned row ...
+    force_levels = ("fp32_f16", "fp32_f16x2")  # ... at these cascade levels
 
     @staticmethod
     def _sims(feature, bank_shard, mode):
-        q = feature.numpy()
-        if mode == "f16x2":  # the candidate pass: fp16-rounded queries (one-sided 2^-11 operand error)
+        q, b = feature.numpy(), bank_shard.numpy()
+        if mode in ("f16", "f16x2"):  # the candidate passes: fp16-rounded queries (2^-11 operand error) ...
             q = q.astype(np.float16).astype(np.float32)
-        return O.sims_seqfma(q, bank_shard.numpy())
+        if mode == "f16":             # ... and, at the first level, an fp16-rounded bank as well
+            b = b.astype(np.float16).astype(np.float32)
+        return O.sims_seqfma(q, b)
 
     @classmethod
     def topk_keys(cls, feature, bank_shard, k, mode, idx_offset, tau0=None):
@@ -83,9 +86,11 @@ class OracleOps:
 
     # ---- sharded fp32 mode (same contract as _CudaOps)
     @staticmethod
-    def first_level(bank_shard, mode):
+    def cascade_levels(bank_shard, mode):
         from b200knn.knn import LEVELS
-        return dict(LEVELS["fp32_f16x2"], name="fp32_f16x2") if mode == "fp32" else None
+        if mode != "fp32":
+            return None
+        return [dict(LEVELS[name], name=name) for name in ("fp32_f16", "fp32_f16x2")]
 
     @staticmethod
     def route_keys(keys, rows_per_shard, n_shards):
@@ -119,7 +124,7 @@ class OracleOps:
         e = level["err_coef"] * qn * m + level.get("err_abs", 0.0) * np.sqrt(feature.shape[1]) * (qn + m)
         ok = np.isfinite(es[:, -1]) & (es[:, -1] > as_[:, -1] + e)
         ok = np.where(np.isneginf(as_[:, -1]), bool(all_rows), ok)
-        if cls.force_uncertified and ok.size:
+        if cls.force_uncertified and ok.size and level["name"] in cls.force_levels:
             ok[0] = False
         return torch.from_numpy((~ok).astype(np.int32))
 
