@@ -399,7 +399,9 @@ def main():
         pk = peaks()
         ms_per_step = total_ms / args.steps
         value = Q / (ms_per_step * 1e-3)
-        kern = sum(kern_ms) / max(1, len(kern_ms))
+        # time of the similarity + top-k calls of one step (main pass; in the fp32 cascade also the
+        # small second-level pass over the rows the first level could not certify)
+        kern = sum(kern_ms) / max(1, args.steps)
         flops = 2.0 * Q * n_local * DIM  # algorithmic: 2*N*D per query, this rank's rows
         achieved = flops / (kern * 1e-3) / 1e12
         cand_mode = K.RESCORED_MODES[mode]["cand"] if mode in K.RESCORED_MODES else mode
