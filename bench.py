@@ -393,7 +393,10 @@ def main():
         step_resident()
         torch.cuda.synchronize()
         log, sb.phase_log = sb.phase_log, None
-        phases = {log[i][0]: round(log[i - 1][1].elapsed_time(log[i][1]), 3) for i in range(1, len(log))}
+        phases = {}
+        for i in range(1, len(log)):  # same-named phases (cascade levels) are summed
+            if log[i][0] != "start":
+                phases[log[i][0]] = round(phases.get(log[i][0], 0.0) + log[i - 1][1].elapsed_time(log[i][1]), 3)
 
     if rank == 0:
         pk = peaks()
