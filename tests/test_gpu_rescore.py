@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _rescore(q, rows_pad, cand, N, D, k_out, idx_offset, err_coef, max_norm, use_ws, all_flags=False):
+def _rescore(q, rows_pad, cand, N, D, k_out, idx_offset, err_coef, max_norm, use_ws):
     lib = _lib.load()
     B, k_in = cand.shape
     out = torch.zeros((B, k_out), dtype=torch.int64, device=DEV)
