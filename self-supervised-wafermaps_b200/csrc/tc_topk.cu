@@ -463,13 +463,21 @@ __global__ void __launch_bounds__(kThreads, 1)
               my_list[st.cnt] = make_key(mx, gidx0 + uint32_t(__ffs(m) - 1));
               st.cnt += 1;
             } else {
+              // several candidates: walk only the column classes that hold one (the list is
+              // unordered until its prune / flush, so the class-major append order is immaterial)
               uint64_t* lp = my_list + st.cnt;
               uint32_t c = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if ((m >> j) & 1u) {
-                  lp[c] = make_key(s[j], gidx0 + uint32_t(j));
-                  ++c;
+              for (int cl = 0; cl < 4; ++cl) {
+                const unsigned mc = m & (0x11111111u << cl);
+                if (mc != 0u) {
+#pragma unroll
+                  for (int j = cl; j < 32; j += 4) {
+                    if ((mc >> j) & 1u) {
+                      lp[c] = make_key(s[j], gidx0 + uint32_t(j));
+                      ++c;
+                    }
+                  }
                 }
               }
               st.cnt += c;
