@@ -375,7 +375,7 @@ class ShardedBank:
 
     def _global_max_norm(self, cand_mode: str) -> torch.Tensor:
         """max row norm over the WHOLE bank (all-reduce MAX of the shards' values), cached."""
-        key = ("max_norm", cand_mode)
+        key = ("max_norm", cand_mode, getattr(self.bank_shard, "_version", 0))  # in-place bank updates
         hit = self._symm.get(key)
         if hit is None:
             hit = self.ops.bank_max_norm(self.bank_shard, cand_mode).clone()
