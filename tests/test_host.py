@@ -95,3 +95,25 @@ def test_shard_bounds_cover_and_are_disjoint():
 
 def test_padded_dim():
     assert [K.padded_dim(d) for d in (1, 64, 72, 384, 512, 768)] == [64, 64, 128, 384, 512, 768]
+
+
+def test_bench_inputs_are_shard_reproducible():
+    """bench.py generates the synthetic bank in 65,536-row chunks with one generator per chunk, so a
+    rank that only materialises its own rows (sharded runs, config c5) gets exactly the rows of the
+    full bank, and the replicated labels / queries do not depend on the shard."""
+    import sys
+
+    import torch
+
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    n, q, d = 150000, 37, 16
+    full_bank, full_lab, full_q = bench.make_inputs("cpu", n, q, d, seed=3)
+    assert full_bank.shape == (n, d) and full_lab.shape == (n,) and full_q.shape == (q, d)
+    assert torch.allclose(full_bank.norm(dim=1), torch.ones(n), atol=1e-5)
+    for lo, hi in ((0, 50000), (50000, 100000), (100000, 150000), (65530, 65540)):
+        bank, lab, qq = bench.make_inputs("cpu", n, q, d, seed=3, row_range=(lo, hi))
+        assert torch.equal(bank, full_bank[lo:hi]) and torch.equal(lab, full_lab) and torch.equal(qq, full_q)
