@@ -117,3 +117,45 @@ def test_bench_inputs_are_shard_reproducible():
     for lo, hi in ((0, 50000), (50000, 100000), (100000, 150000), (65530, 65540)):
         bank, lab, qq = bench.make_inputs("cpu", n, q, d, seed=3, row_range=(lo, hi))
         assert torch.equal(bank, full_bank[lo:hi]) and torch.equal(lab, full_lab) and torch.equal(qq, full_q)
+
+
+def test_fp16_candidate_levels_operand_error_bounds():
+    """The rigorous (operand-rounding) part of the certificate coefficients of the fp16 candidate
+    levels (b200knn/knn.py LEVELS): with fp16-rounded operands and EXACT accumulation,
+        f16  : |q16.x16 - q.x|          <= 2^-10 (1+2^-12) |q||x| + 2^-25 sqrt(D) (|q|+|x|)
+        f16x2: |q16.(x_hi+x_lo) - q.x|  <= (2^-11 + 2^-22)(1+2^-11) |q||x| + 2^-25 sqrt(D) (|q|+|x|)
+    including fp16's subnormal range (the 2^-25 terms).  The levels' err_coef / err_abs must dominate
+    these (the remainder of err_coef is the stated allowance for the fp32 accumulation in TMEM)."""
+    import numpy as np
+
+    from b200knn.knn import LEVELS
+
+    rng = np.random.default_rng(0)
+    D = 512
+    worst = {"f16": 0.0, "f16x2": 0.0}
+    for scale_q, scale_x in [(1.0, 1.0), (1e-3, 1.0), (1.0, 1e-4), (3e-4, 3e-4), (50.0, 200.0), (1e-5, 1e-5)]:
+        q = (rng.standard_normal((64, D)) * scale_q / np.sqrt(D)).astype(np.float32)
+        x = (rng.standard_normal((256, D)) * scale_x / np.sqrt(D)).astype(np.float32)
+        q[0] = np.abs(q[0])  # aligned signs: rounding errors add up instead of cancelling
+        x[0] = np.abs(x[0])
+        q16 = q.astype(np.float16).astype(np.float64)
+        x_hi = x.astype(np.float16)
+        x_lo = (x - x_hi.astype(np.float32)).astype(np.float16)
+        exact = q.astype(np.float64) @ x.astype(np.float64).T
+        qn = np.linalg.norm(q.astype(np.float64), axis=1)[:, None]
+        xn = np.linalg.norm(x.astype(np.float64), axis=1)[None, :]
+        tail = 2.0 ** -25 * np.sqrt(D) * (qn + xn)
+        for name, approx, coef in (
+                ("f16", q16 @ x_hi.astype(np.float64).T, 2.0 ** -10 * (1 + 2.0 ** -12)),
+                ("f16x2", q16 @ (x_hi.astype(np.float64) + x_lo.astype(np.float64)).T,
+                 (2.0 ** -11 + 2.0 ** -22) * (1 + 2.0 ** -11))):
+            err = np.abs(approx - exact)
+            bound = coef * qn * xn + tail
+            assert (err <= bound).all(), (name, scale_q, scale_x, float((err / bound).max()))
+            worst[name] = max(worst[name], float((err / bound).max()))
+            lv = LEVELS["fp32_" + name]
+            assert lv["err_coef"] >= coef and lv["err_abs"] >= 2.0 ** -25 and lv["max_abs"] < 65504.0
+            # the certificate's E (host side multiplies err_abs by sqrt(padded D)) dominates the bound
+            e_cert = lv["err_coef"] * qn * xn + lv["err_abs"] * np.sqrt(D) * (qn + xn)
+            assert (e_cert >= bound).all()
+    print("largest observed error / rigorous bound:", worst)
