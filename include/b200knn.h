@@ -33,7 +33,8 @@
 extern "C" {
 #endif
 
-#define B200KNN_VERSION 130 /* 0.1.3: + B200KNN_MODE_F16; 0.1.2: + b200knn_route_keys, b200knn_certify (sharded fp32 mode); 0.1.1: b200knn_rescore workspace */
+#define B200KNN_VERSION 140 /* 0.1.4: + b200knn_topk_exact_below (k > 992), b200knn_route_scatter, b200knn_rescore_scatter,
+                              b200knn_compact_rows, b200knn_scatter_rows (sync-free sharded fp32 mode); 0.1.3: + B200KNN_MODE_F16; 0.1.2: + b200knn_route_keys, b200knn_certify (sharded fp32 mode); 0.1.1: b200knn_rescore workspace */
 
 /* error codes */
 #define B200KNN_OK 0
@@ -122,6 +123,17 @@ int b200knn_topk(int mode,
  * the true k-th similarity except with negligible probability; the host shim
  * detects the exception (empty k-th slot) and recomputes that row without tau0.
  */
+/*
+ * Tensor.topk accepts any k <= N; the streaming lists hold at most 992 keys.  Larger k is served in
+ * passes of <= 992 ("peeling"): b200knn_topk in MODE_EXACT restricted to keys strictly below
+ * upper_keys[b] (the last key of row b from the previous pass; nullptr = no bound).  Arguments as
+ * b200knn_topk.
+ */
+int b200knn_topk_exact_below(const void* q, int q_dtype, int64_t q_ld, const void* bank, int bank_dtype,
+                             int bank_layout, int64_t bank_ld, int64_t B, int64_t N, int dim, int k,
+                             int64_t idx_offset, const uint64_t* upper_keys, uint64_t* out_keys,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo,
                     const void* bank_hi, const void* bank_lo, int64_t B,
                     int64_t n_visit, int dim, int k, int64_t idx_offset,
@@ -266,6 +278,33 @@ int b200knn_certify(const void* q, int q_dtype, int64_t q_ld, int dim, const uin
                     const uint64_t* approx_keys, int k_in, int64_t B, int all_rows, float err_coef,
                     float err_abs, float max_abs, const float* bank_max_norm, int32_t* uncertified,
                     int32_t* n_uncertified, void* stream);
+
+/*
+ * The same exchange without NCCL round trips or host synchronisation (peer memory over NVLink):
+ * b200knn_route_scatter: b200knn_route_keys fused with its all-to-all — the candidates of owned query
+ *   row r that shard g can re-score are stored, compacted, into row (row_offset + r) of shard g's
+ *   inbox host_inbox[g] (a (Q_pad, k) buffer of every rank, mapped here; the receivers zero their
+ *   inboxes before the barrier that precedes the call).  n_shards <= 8.
+ * b200knn_rescore_scatter: b200knn_rescore (fp32 queries, one fp32 row array, k_out = k_in, no
+ *   certificate) whose sorted exact keys of query row b go straight into the exchange buffer of
+ *   the GPU that owns b: host_peer_out[b / rows_per_owner] + ((my_rank * rows_per_owner +
+ *   b % rows_per_owner) * k_in); only non-empty slots are written (receivers zero their buffers).
+ * b200knn_compact_rows: rows_out[0..min(count,cap)) = ascending row numbers i with
+ *   (status[i*ld] & mask) != 0, the rest of rows_out = 0, *count_out = their number (may exceed
+ *   cap): the rows a cascade level could not certify, chosen on the device so that the next level
+ *   runs on a fixed-capacity sub-batch without a host read.
+ * b200knn_scatter_rows: dst[rows[i]*dst_ld + c] = src[i*src_ld + c], c < width, i < min(n, *count).
+ */
+int b200knn_route_scatter(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int n_shards,
+                          const void* const* host_inbox, int64_t row_offset, void* stream);
+int b200knn_rescore_scatter(const float* q, int64_t q_ld, const float* rows, int64_t N, int dim,
+                            const uint64_t* cand_keys, int64_t B, int k_in, int64_t idx_offset,
+                            const void* const* host_peer_out, int n_peers, int my_rank,
+                            int64_t rows_per_owner, void* workspace, size_t workspace_bytes, void* stream);
+int b200knn_compact_rows(const int64_t* status, int64_t ld, int64_t n, int64_t mask, int64_t* rows_out,
+                         int cap, int32_t* count_out, void* stream);
+int b200knn_scatter_rows(int64_t* dst, int64_t dst_ld, const int64_t* src, int64_t src_ld,
+                         const int64_t* rows, int n, const int32_t* count, int width, void* stream);
 
 /*
  * SURVEY.md §8(f) rows — the steps either side of knn_predict in the reference.

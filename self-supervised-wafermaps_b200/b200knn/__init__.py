@@ -31,6 +31,7 @@ from .knn import (  # noqa: F401
 )
 from .knn import normalize_rows, row_sqnorms, vote_packed  # noqa: F401
 from .bank import FeatureBank  # noqa: F401
+from .hooks import install_hooks, uninstall_hooks  # noqa: F401
 from .metrics import confusion_counts, knn_metrics, metrics_from_counts  # noqa: F401
 from .retrieval import L2Index, knn_graph, l2_topk, load_embedding_table  # noqa: F401
 from .sharded import ShardedBank, shard_bounds  # noqa: F401

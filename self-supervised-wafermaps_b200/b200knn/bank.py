@@ -53,22 +53,42 @@ class FeatureBank:
         return cls(padded, dim, labels)
 
     @classmethod
-    def from_batches(cls, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]],
-                     normalize: bool = True) -> "FeatureBank":
+    def from_batches(cls, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], normalize: bool = True,
+                     total_rows: Optional[int] = None) -> "FeatureBank":
         """The loop of ``on_validation_epoch_start`` (``knn.py:70-81``): (features, targets) per
-        dataloader batch; each batch is normalised + laid out as it arrives."""
-        rows: List[torch.Tensor] = []
-        labs: List[torch.Tensor] = []
+        dataloader batch.  Each batch is normalised and laid out by one kernel straight into its
+        slice of ONE (N, D_pad) buffer — the reference's list of per-batch tensors, its ``torch.cat``
+        copy and its ``.t().contiguous()`` copy never exist.  total_rows (``len(dataloader.dataset)``)
+        sizes the buffer up front; without it (or if more rows arrive) the buffer grows geometrically."""
+        buf: Optional[torch.Tensor] = None
+        labs: Optional[torch.Tensor] = None
+        n = 0
         dim = None
         for feat, target in batches:
             K._require_cuda("feature batch", feat)
-            dim = feat.shape[1]
-            rows.append(K.normalize_rows(feat)._base if normalize
-                        else K.prepare_rows(feat, "f32rows", vectors_are_columns=False).hi)
-            labs.append(target.to(feat.device).long().view(-1))
+            if feat.dim() != 2:
+                raise RuntimeError("feature batches must be (b, D)")
+            b = feat.shape[0]
+            if dim is None:
+                dim = feat.shape[1]
+                cap = max(int(total_rows or 0), b)
+                buf = torch.empty((cap, K.padded_dim(dim)), dtype=torch.float32, device=feat.device)
+                labs = torch.empty((cap,), dtype=torch.int64, device=feat.device)
+            elif feat.shape[1] != dim:
+                raise RuntimeError(f"feature batch has dimension {feat.shape[1]}, expected {dim}")
+            if n + b > buf.shape[0]:
+                cap = max(n + b, 2 * buf.shape[0])
+                buf = torch.cat([buf[:n], torch.empty((cap - n, buf.shape[1]), dtype=buf.dtype, device=buf.device)])
+                labs = torch.cat([labs[:n], torch.empty((cap - n,), dtype=labs.dtype, device=labs.device)])
+            if normalize:
+                K.normalize_rows(feat, out=buf[n:n + b])
+            else:
+                buf[n:n + b] = K.prepare_rows(feat, "f32rows", vectors_are_columns=False).hi
+            labs[n:n + b] = target.to(feat.device).view(-1)
+            n += b
         if dim is None:
             raise RuntimeError("no batches")
-        return cls(torch.cat(rows, 0), dim, torch.cat(labs, 0))
+        return cls(buf[:n], dim, labs[:n])
 
     # ------------------------------------------------------------------ the reference's calls
     @property

@@ -27,9 +27,16 @@ _PROVIDERS = ("lightly.utils.benchmarking", "lightly.utils.benchmarking.knn")
 _CONSUMERS = ("ssl_wafermap.models.knn",)
 
 
-def install(extra_consumers: Tuple[str, ...] = ()) -> Dict[str, bool]:
+def install(extra_consumers: Tuple[str, ...] = (), hooks: bool = False,
+            hook_classes: Tuple[type, ...] = ()) -> Dict[str, bool]:
     """Rebind ``knn_predict`` everywhere the reference looks it up.  Returns which
-    modules were patched.  Idempotent; ``uninstall()`` restores the originals."""
+    modules were patched.  Idempotent; ``uninstall()`` restores the originals.
+
+    hooks=True additionally replaces the validation hooks of the reference's
+    ``KNNBenchmarkModule`` / ``WandBKNNBenchmarkModule`` (``src/ssl_wafermap/models/knn.py:67-133``,
+    ``:181-215``) by the fused bank build / query normalise / on-device metrics of
+    ``b200knn.hooks``; hook_classes names further classes with the same
+    hook interface (e.g. the copy ``scripts/WM811k_benchmark.py`` defines)."""
     from .knn import knn_predict
 
     done: Dict[str, bool] = {}
@@ -65,6 +72,10 @@ def install(extra_consumers: Tuple[str, ...] = ()) -> Dict[str, bool]:
         _saved.append((main, "knn_predict", getattr(main, "knn_predict")))
         setattr(main, "knn_predict", knn_predict)
         done["__main__"] = True
+    if hooks or hook_classes:
+        from .hooks import install_hooks
+
+        done.update(install_hooks(hook_classes))
     return done
 
 
@@ -72,10 +83,13 @@ def uninstall() -> None:
     while _saved:
         mod, attr, orig = _saved.pop()
         setattr(mod, attr, orig)
+    from .hooks import uninstall_hooks
+
+    uninstall_hooks()
 
 
 if os.environ.get("B200KNN_AUTOINSTALL") == "1":  # pragma: no cover - exercised via subprocess test
     try:
-        install()
+        install(hooks=os.environ.get("B200KNN_HOOKS") == "1")
     except Exception:
         pass

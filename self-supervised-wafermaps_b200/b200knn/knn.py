@@ -38,44 +38,83 @@ MAX_BF16_DIM = 768  # widest (padded) vector whose query tile the BF16 kernel ca
 
 _default_mode = os.environ.get("B200KNN_MODE", "fp32")
 
-# Measurement hook (bench.py): when set to a list, every b200knn_topk C call is bracketed by
-# CUDA events recorded on the launching stream and the (start, end) pair is appended.
+# Measurement hook (bench.py): when set to a dict, the similarity + top-k C calls ("topk") and the
+# exact re-scoring calls ("rescore") are bracketed by CUDA events recorded on the launching stream
+# and the (start, end) pairs are appended to the list under that name.
 profile_events = None
+
+
+class _Timed:
+    """with _Timed("topk"): <C call>  — no-op unless bench.py switched profile_events on."""
+
+    __slots__ = ("name", "ev")
+
+    def __init__(self, name: str, on: bool = True):
+        self.name = name
+        self.ev = None
+        if on and profile_events is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    def __enter__(self):
+        if self.ev is not None:
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            profile_events.setdefault(self.name, []).append(self.ev)
+        return False
 
 
 # "fp32" modes: tensor-core candidate generation + exact re-scoring (csrc/rescore.cu) + a per-row
 # certificate; uncertified rows fall through to the next level and finally to the exact kernel, so
 # every one of these modes returns bit for bit the "exact" keys.
-#   level: candidate mode, extra candidates kept beyond k, error coefficient of the certificate
-#   (|approx - exact| <= coef * ||q|| * max||bank row||):
-#   bf16  : 2^-7 is the rigorous Cauchy-Schwarz bound of the two operand roundings (unit roundoff
-#           2^-8 each); +2 % covers their product term and the fp32 accumulation.  The wide margin
-#           (k+128 candidates) is what lets the certificate pass: it needs the exact k-th similarity
-#           to beat the approximate (k+128)-th by 2^-7.
-#   tf32x3: operand error 2^-20 (dropped lo*lo, truncated lo) is rigorous; the fp32 accumulation in
-#           TMEM is not IEEE, so 2e-5 is an EMPIRICAL bound, ~10x the largest error observed.
-#   bf16x3: operands hi + lo with |x - hi - lo| <= 2^-16 |x| each and the dropped lo*lo term
-#           (2^-16): 3 * 2^-16 = 4.6e-5 is rigorous; 6e-5 leaves the same empirical allowance for
-#           the accumulation as tf32x3.
-#   f16x2 : fp16 queries x (fp16 hi + fp16 lo) bank, two MMAs per k-step.  Rigorous operand part:
-#           |q_i - fp16(q_i)| <= 2^-11 |q_i| + 2^-25 and |x_i - hi_i - lo_i| <= 2^-22 |x_i| + 2^-25
-#           (the 2^-25 terms cover fp16's subnormal range), hence
-#           |error| <= (2^-11 + 2^-22) ||q|| ||x|| + 2^-25 sqrt(D) (||q|| + ||x||)  = err_coef, err_abs;
-#           2e-5 is the same empirical accumulation allowance as above.  Operands at or beyond
-#           fp16's range (max_abs) are refused.  The one-sided 2^-11 needs k+40 candidates where the
-#           split modes need k+16, and buys a third fewer MMAs than bf16x3 on CTA pairs.
-#   f16   : fp16 x fp16, one MMA per k-step (the BF16 kernel's speed).  Both operands are rounded:
-#           |error| <= 2^-10 (1 + 2^-12) ||q|| ||x|| + 2^-25 sqrt(D) (||q|| + ||x||); with k+40
-#           candidates ~99 % of the rows of the 811k x 512 workload certify, the rest goes to f16x2.
+#
+# Certificate bound of a level: |approx - exact| <= err_coef * ||q|| * max||bank row||
+#                                                   + err_abs * sqrt(D_pad) * (||q|| + max||bank row||)
+# with err_coef = op_coef + acc_c * D_pad * 2^-23.
+#
+# op_coef — operand rounding, RIGOROUS (Cauchy-Schwarz on the element-wise rounding errors; checked
+# element by element in tests/test_host.py::test_fp16_operand_rounding_bounds):
+#   f16   : both operands rounded to fp16: 2^-10 (1 + 2^-12), + err_abs 2^-25 per element for
+#           fp16's subnormal range; operands at or beyond max_abs are refused (saturation);
+#   f16x2 : fp16 queries x (fp16 hi + fp16 lo) bank: 2^-11 + 2^-22 (only the query keeps 11 bits);
+#   bf16  : 2^-7 (two roundings of unit roundoff 2^-8) x 1.02 for their product term;
+#   bf16x3: hi + lo operands, |x - hi - lo| <= 2^-16 |x| each + the dropped lo*lo term: 3 * 2^-16;
+#   tf32x3: 2^-20 (dropped lo*lo, truncated lo).
+# acc_c * D_pad * 2^-23 — accumulation in the tensor core, WORST CASE under this model of
+# tcgen05.mma (validated by tests/test_gpu_tc.py::test_tmem_accumulation_error_bound on all-positive
+# and adversarial operands at D = 512 / 768 / 1024): the K products of one instruction (K = 16 for
+# kind::f16, 8 for kind::tf32) are exact; they and the fp32 accumulator are aligned to the largest
+# exponent among them, each addend loses less than one unit in the last place of that binade
+# (truncation, no guard bits assumed), and the normalised result loses less than one more.  One
+# instruction therefore errs by at most (K + 2) * 2^-23 * A, A = sum_i |q_i x_i| <= ||q|| ||x||,
+# and a similarity is n_mma = (MMAs per k-step) * D_pad / K chained instructions:
+#       acc error <= n_mma * (K + 2) * 2^-23 * ||q|| ||x||  =  acc_c * D_pad * 2^-23 * ||q|| ||x||,
+#   acc_c = (MMAs per k-step) * (K + 2) / K:  f16, bf16 1.125;  f16x2 2.25;  bf16x3 3.375;  tf32x3 3.75.
+# Unlike round 1's flat 2e-5 this grows with D and holds for same-sign products (the reference's
+# live embeddings are non-negative: timm ResNet-18 pooled post-ReLU, knn.py:322), where truncation
+# errors do not cancel: 6.9e-5 (f16) ... 2.3e-4 (tf32x3) at D = 512.
+ACC_ULP = 2.0 ** -23
 LEVELS = {
-    "fp32_f16": dict(cand="f16", margin=40, err_coef=1.001 * 2.0 ** -10 + 2e-5,
+    "fp32_f16": dict(cand="f16", margin=40, op_coef=1.001 * 2.0 ** -10, acc_c=1.125,
                      err_abs=1.01 * 2.0 ** -25, max_abs=6.0e4),
-    "fp32_f16x2": dict(cand="f16x2", margin=40, err_coef=1.001 * (2.0 ** -11 + 2.0 ** -22) + 2e-5,
+    "fp32_f16x2": dict(cand="f16x2", margin=40, op_coef=1.001 * (2.0 ** -11 + 2.0 ** -22), acc_c=2.25,
                        err_abs=1.01 * 2.0 ** -25, max_abs=6.0e4),
-    "fp32_bf16": dict(cand="bf16", margin=128, err_coef=1.02 * 2.0 ** -7),
-    "fp32_bf16x3": dict(cand="bf16x3", margin=16, err_coef=6e-5),
-    "fp32_tf32": dict(cand="tf32x3", margin=8, err_coef=2e-5),
+    "fp32_bf16": dict(cand="bf16", margin=128, op_coef=1.02 * 2.0 ** -7, acc_c=1.125),
+    "fp32_bf16x3": dict(cand="bf16x3", margin=16, op_coef=1.001 * 3 * 2.0 ** -16, acc_c=3.375),
+    "fp32_tf32": dict(cand="tf32x3", margin=8, op_coef=1.001 * 2.0 ** -20, acc_c=3.75),
 }
+
+
+def level_config(name: str, dim: int) -> dict:
+    """LEVELS[name] with the certificate's err_coef resolved for vectors of dimension `dim`."""
+    cfg = dict(LEVELS[name], name=name)
+    cfg["err_coef"] = cfg["op_coef"] + 1.01 * cfg["acc_c"] * padded_dim(dim) * ACC_ULP
+    return cfg
+
+
 # mode -> levels tried in order (then "exact").  "fp32" skips its BF16 level for a bank on which
 # that level recently left more than CASCADE_GIVE_UP of the rows uncertified.
 CASCADES = {"fp32": ("fp32_f16", "fp32_f16x2", "fp32_bf16x3", "fp32_tf32"), "fp32_f16": ("fp32_f16",),
@@ -84,12 +123,15 @@ CASCADES = {"fp32": ("fp32_f16", "fp32_f16x2", "fp32_bf16x3", "fp32_tf32"), "fp3
             "fp32_bf16": ("fp32_bf16",), "fp32_tf32": ("fp32_tf32",)}
 CASCADE_GIVE_UP = 0.25
 CASCADE_RETRY_CALLS = 64
+# The cascade's first level is skipped for CASCADE_RETRY_CALLS calls on a bank where it left more
+# than CASCADE_GIVE_UP of the rows uncertified (single-GPU path only: the sharded driver derives
+# every decision from all-gathered data, never from per-process state).
 # first level of each mode (bench / docs)
 RESCORED_MODES = {m: LEVELS[c[0]] for m, c in CASCADES.items()}
 ALL_MODES = tuple(_lib.MODES) + tuple(RESCORED_MODES)
 
 # statistics of the last rescored call (bench / tests): rows that failed the certificate
-last_rescore_stats = {"rows": 0, "uncertified": 0, "level": None}
+last_rescore_stats = {"rows": 0, "uncertified": 0, "level": None, "levels": []}
 
 
 def set_default_mode(mode: str) -> None:
@@ -138,6 +180,15 @@ def _require_cuda(name: str, t: torch.Tensor) -> None:
 
 def padded_dim(dim: int) -> int:
     return (dim + 63) // 64 * 64
+
+
+def effective_mode(mode: str, dim: int) -> str:
+    """The kernel mode a raw tensor-core mode runs as for vectors of dimension `dim`: bf16 / f16 /
+    f16x2 keep a 128-row query tile resident in shared memory (D_pad * 256 B), so wider vectors
+    go through the split-BF16 kernel, which streams both operands (and is more accurate)."""
+    if mode in ("bf16", "f16x2", "f16") and padded_dim(dim) > MAX_BF16_DIM:
+        return "bf16x3"
+    return mode
 
 
 # ----------------------------------------------------------------------------
@@ -194,9 +245,10 @@ def register_padded_rows(bank_view: torch.Tensor, rows_padded: torch.Tensor) -> 
     _padded_rows[(bank_view.data_ptr(), tuple(bank_view.shape), tuple(bank_view.stride()))] = weakref.ref(rows_padded)
 
 
-def normalize_rows(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+def normalize_rows(x: torch.Tensor, eps: float = 1e-12, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``F.normalize(x, dim=1)`` of (n, D) rows (reference ``knn.py:77`` / ``:90``) into zero-padded
-    fp32 rows; returns the (n, D) view of the (n, D_pad) result.  fp64 norm in a fixed order."""
+    fp32 rows; returns the (n, D) view of the (n, D_pad) result.  fp64 norm in a fixed order.
+    out: optional contiguous (n, D_pad) fp32 destination (a slice of a preallocated bank)."""
     _require_cuda("x", x)
     if x.dim() != 2:
         raise RuntimeError("normalize_rows expects (n, D) row vectors")
@@ -205,7 +257,11 @@ def normalize_rows(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     if x.stride(1) != 1:
         x = x.contiguous()
     n, dim = x.shape
-    out = torch.empty((n, padded_dim(dim)), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((n, padded_dim(dim)), dtype=torch.float32, device=x.device)
+    elif out.shape != (n, padded_dim(dim)) or out.dtype != torch.float32 or not out.is_contiguous() \
+            or out.device != x.device:
+        raise ValueError("out must be a contiguous (n, padded_dim(D)) fp32 tensor on the rows' device")
     if n:
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().b200knn_normalize_rows(x.data_ptr(), _DTYPES[x.dtype], n, dim, x.stride(0),
@@ -302,6 +358,10 @@ class _BankCache:
         hit = self._entries.get(key)
         if hit is not None and hit[0]() is not None:
             return hit[1]
+        # the reference rebuilds its bank every validation epoch (knn.py:80): drop the prepared
+        # copies (several GB at 811k x 512) of banks that no longer exist before preparing a new one
+        for dead in [k_ for k_, v in self._entries.items() if v[0]() is None]:
+            self._entries.pop(dead)
         if mode == "f16":
             # fp16(x) is the hi array of the f16x2 split (the next cascade level): share it
             both = self.get(bank, "f16x2")
@@ -413,16 +473,10 @@ def _tc_call(mode, pq, pb, B, n_visit, D, k, idx_offset, stride, tau0, dev, time
                                            _ptr(pb.lo), B, n_visit, D, stride, keys.data_ptr(), ws.data_ptr(),
                                            ws_bytes, _stream()), "topk_sample")
         return keys
-    ev = None
-    if timed and profile_events is not None:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-    rc = lib.b200knn_topk_ex(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(), _ptr(pb.lo),
-                             B, n_visit, D, k, idx_offset, stride, _ptr(tau0), keys.data_ptr(),
-                             ws.data_ptr(), ws_bytes, _stream())
-    if ev is not None:
-        ev[1].record()
-        profile_events.append(ev)
+    with _Timed("topk", timed):
+        rc = lib.b200knn_topk_ex(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(), _ptr(pb.lo),
+                                 B, n_visit, D, k, idx_offset, stride, _ptr(tau0), keys.data_ptr(),
+                                 ws.data_ptr(), ws_bytes, _stream())
     _lib.check(rc, "topk")
     return keys
 
@@ -468,6 +522,7 @@ def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode:
     if s == 0 or mode not in TC_MODES:
         return None
     B, D = feature.shape
+    mode = effective_mode(mode, D)
     r = PREPASS["r"]
     n_visit = (N + s - 1) // s
     if n_visit < r:
@@ -491,16 +546,18 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
     threshold starved (empty k-th slot); the caller detects and repairs them (``repair_rows``)."""
     lib = _lib.load()
     mode = mode or _default_mode
+    if mode not in _lib.MODES and mode not in RESCORED_MODES:
+        raise ValueError(f"unknown mode {mode!r}")
+    if int(k) > MAX_K:
+        # Tensor.topk takes any k <= N; the streaming lists hold MAX_K keys.  Larger k is served by
+        # the exact kernel in passes of <= MAX_K (a completeness path, whatever the mode).
+        _check_feature_bank(feature, feature_bank)
+        return _topk_keys_peeled(feature, feature_bank, int(k), idx_offset)
     if mode in RESCORED_MODES:
         return _topk_keys_rescored(feature, feature_bank, k, mode, idx_offset)
-    if mode not in _lib.MODES:
-        raise ValueError(f"unknown mode {mode!r}")
     _check_feature_bank(feature, feature_bank)
     B, D = feature.shape
-    if mode in ("bf16", "f16x2", "f16") and padded_dim(D) > MAX_BF16_DIM:
-        # these kernels keep a 128-row query tile resident in shared memory (D_pad * 256 B);
-        # wider vectors go through the split kernel, which streams both operands
-        mode = "bf16x3"
+    mode = effective_mode(mode, D)
     N = feature_bank.shape[1]
     k = int(k)
     if k <= 0 or k > N:
@@ -520,17 +577,11 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
                 q = q.contiguous()
             bank = feature_bank if feature_bank.dtype in _DTYPES else feature_bank.float()
             bank, layout, ld = _layout_of(bank, vectors_are_columns=True)
-            ev = None
-            if profile_events is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            rc = lib.b200knn_topk(_lib.MODE_EXACT, q.data_ptr(), None, _DTYPES[q.dtype], q.stride(0),
-                                  bank.data_ptr(), None, _DTYPES[bank.dtype], layout, ld,
-                                  B, N, D, k, idx_offset, keys.data_ptr(), ws.data_ptr(), ws_bytes,
-                                  _stream())
-            if ev is not None:
-                ev[1].record()
-                profile_events.append(ev)
+            with _Timed("topk"):
+                rc = lib.b200knn_topk(_lib.MODE_EXACT, q.data_ptr(), None, _DTYPES[q.dtype], q.stride(0),
+                                      bank.data_ptr(), None, _DTYPES[bank.dtype], layout, ld,
+                                      B, N, D, k, idx_offset, keys.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      _stream())
             _lib.check(rc, "topk")
             return keys
         pb = bank_cache.get(feature_bank, mode)
@@ -547,6 +598,43 @@ def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: O
                                                         idx_offset, 1, None, dev))
 
 
+def _topk_keys_peeled(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, idx_offset: int) -> torch.Tensor:
+    """Exact keys for k > MAX_K: pass i selects the best min(MAX_K, remaining) keys strictly below
+    the last key of pass i-1 (b200knn_topk_exact_below); ceil(k / MAX_K) scans of the bank."""
+    lib = _lib.load()
+    B, D = feature.shape
+    N = feature_bank.shape[1]
+    if k > N:
+        raise RuntimeError("selected index k out of range")
+    dev = feature.device
+    keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+    if B == 0:
+        return keys
+    q = feature if feature.dtype in _DTYPES else feature.float()
+    if q.stride(1) != 1:
+        q = q.contiguous()
+    bank = feature_bank if feature_bank.dtype in _DTYPES else feature_bank.float()
+    bank, layout, ld = _layout_of(bank, vectors_are_columns=True)
+    upper = None
+    done = 0
+    with torch.cuda.device(dev):
+        while done < k:
+            kp = min(MAX_K, k - done)
+            part = torch.empty((B, kp), dtype=torch.int64, device=dev)
+            ws_bytes = lib.b200knn_topk_workspace_bytes(B, N, D, kp, _lib.MODE_EXACT)
+            if ws_bytes == 0:
+                raise RuntimeError(f"b200knn: unsupported problem (B={B}, N={N}, D={D}, k={kp})")
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            _lib.check(lib.b200knn_topk_exact_below(q.data_ptr(), _DTYPES[q.dtype], q.stride(0), bank.data_ptr(),
+                                                    _DTYPES[bank.dtype], layout, ld, B, N, D, kp, idx_offset,
+                                                    _ptr(upper), part.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                    _stream()), "topk_exact_below")
+            keys[:, done:done + kp] = part
+            upper = part[:, -1].contiguous()
+            done += kp
+    return keys
+
+
 def topk_scatter(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str, idx_offset: int,
                  tau0: Optional[torch.Tensor], peer_ptrs, rank: int, rows_per_owner: int) -> bool:
     """Fused top-k + exchange (b200knn_topk_scatter): this shard's keys of query row b are stored
@@ -558,6 +646,7 @@ def topk_scatter(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode
         return False
     _check_feature_bank(feature, feature_bank)
     B, D = feature.shape
+    mode = effective_mode(mode, D)
     N = feature_bank.shape[1]
     G = len(peer_ptrs)
     if B == 0 or k > N or G > 8:
@@ -573,17 +662,11 @@ def topk_scatter(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode
             return False
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         ptrs = (ctypes.c_void_p * G)(*[int(p) for p in peer_ptrs])
-        ev = None
-        if profile_events is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
-        rc = lib.b200knn_topk_scatter(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(),
-                                      _ptr(pb.lo), B, N, D, k, idx_offset,
-                                      _ptr(None if tau0 is None else tau0.contiguous()), ptrs, G, rank,
-                                      rows_per_owner, ws.data_ptr(), ws_bytes, _stream())
-        if ev is not None:
-            ev[1].record()
-            profile_events.append(ev)
+        with _Timed("topk"):
+            rc = lib.b200knn_topk_scatter(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(),
+                                          _ptr(pb.lo), B, N, D, k, idx_offset,
+                                          _ptr(None if tau0 is None else tau0.contiguous()), ptrs, G, rank,
+                                          rows_per_owner, ws.data_ptr(), ws_bytes, _stream())
         _lib.check(rc, "topk_scatter")
     return True
 
@@ -595,6 +678,7 @@ def recompute_rows(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mo
     if mode == "exact" or mode in RESCORED_MODES:
         return topk_keys(sub, feature_bank, k, "exact", idx_offset)
     B, D = sub.shape
+    mode = effective_mode(mode, D)
     with torch.cuda.device(feature.device):
         pb = bank_cache.get(feature_bank, mode)
         pq = prepare_rows(sub, mode, vectors_are_columns=False)
@@ -625,8 +709,8 @@ last_prepass_stats = {"rows": 0, "repaired": 0}
 def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, level: str, idx_offset: int):
     """One cascade level, nothing synchronises: (keys (B,k), uncertified flags (B,) int32, count int32[1])."""
     lib = _lib.load()
-    cfg = LEVELS[level]
     B, D = feature.shape
+    cfg = level_config(level, D)
     N = feature_bank.shape[1]
     # the streaming lists hold at most MAX_K keys: near that limit the margin shrinks (and with it
     # the chance to certify; uncertified rows still end up exact through the next level)
@@ -648,11 +732,13 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
         n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
         ws_bytes = int(lib.b200knn_rescore_workspace_bytes(B, k_in)) if rows_b is None else 0
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
-        _lib.check(lib.b200knn_rescore(q.data_ptr(), _DTYPES[q.dtype], q.stride(0), rows_a.data_ptr(),
-                                       _ptr(rows_b), N, D, cand.data_ptr(), B, k_in, k, idx_offset,
-                                       float(cfg["err_coef"]), float(cfg.get("err_abs", 0.0)) * math.sqrt(padded_dim(D)),
-                                       float(cfg.get("max_abs", 0.0)), max_norm.data_ptr(), out.data_ptr(),
-                                       flags.data_ptr(), n_bad.data_ptr(), _ptr(ws), ws_bytes, _stream()), "rescore")
+        with _Timed("rescore"):
+            rc = lib.b200knn_rescore(q.data_ptr(), _DTYPES[q.dtype], q.stride(0), rows_a.data_ptr(),
+                                     _ptr(rows_b), N, D, cand.data_ptr(), B, k_in, k, idx_offset,
+                                     float(cfg["err_coef"]), float(cfg.get("err_abs", 0.0)) * math.sqrt(padded_dim(D)),
+                                     float(cfg.get("max_abs", 0.0)), max_norm.data_ptr(), out.data_ptr(),
+                                     flags.data_ptr(), n_bad.data_ptr(), _ptr(ws), ws_bytes, _stream())
+        _lib.check(rc, "rescore")
     return out, flags, n_bad
 
 
@@ -660,7 +746,7 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
 # a query, re-scored by the shard that owns each candidate's bank row, merged again and certified
 def cascade_levels(feature_bank: torch.Tensor, mode: str) -> list:
     """The candidate levels a rescored mode tries in order on this bank (LEVELS entries + names)."""
-    return [dict(LEVELS[name], name=name) for name in _cascade_levels(feature_bank, mode)]
+    return [level_config(name, feature_bank.shape[0]) for name in _cascade_levels(feature_bank, mode, track=False)]
 
 
 def route_keys(keys: torch.Tensor, rows_per_shard: int, n_shards: int) -> torch.Tensor:
@@ -706,6 +792,93 @@ def rescore_sparse(feature: torch.Tensor, feature_bank: torch.Tensor, cand: torc
     return out
 
 
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def route_scatter(keys: torch.Tensor, rows_per_shard: int, n_shards: int, inbox_ptrs, row_offset: int) -> None:
+    """route_keys fused with its exchange: the keys of row r that shard g owns go, compacted, into
+    row (row_offset + r) of shard g's inbox (device pointers of every rank's (Q_pad, k) inbox)."""
+    n, k = keys.shape
+    if n:
+        keys = keys.contiguous()
+        with torch.cuda.device(keys.device):
+            _lib.check(_lib.load().b200knn_route_scatter(keys.data_ptr(), n, k, rows_per_shard, n_shards,
+                                                         _ptr_array(inbox_ptrs), row_offset, _stream()),
+                       "route_scatter")
+
+
+def rescore_scatter(feature: torch.Tensor, feature_bank: torch.Tensor, cand: torch.Tensor, cand_mode: str,
+                    idx_offset: int, peer_ptrs, rank: int, rows_per_owner: int) -> None:
+    """rescore_sparse whose sorted exact keys of query row b are stored straight into the exchange
+    buffer of the GPU that owns b (peer memory; the owners zero their buffers beforehand)."""
+    lib = _lib.load()
+    B, D = feature.shape
+    if B == 0:
+        return
+    N = feature_bank.shape[1]
+    k_in = cand.shape[1]
+    dev = feature.device
+    pb = bank_cache.get(feature_bank, effective_mode(cand_mode, D))
+    rows_a, rows_b = pb.rescore_rows()
+    if rows_b is not None:  # tf32x3 operands (hi + lo): reassemble once
+        rows_a = rows_a + rows_b
+    q = feature if feature.dtype == torch.float32 else feature.float()
+    if q.stride(1) != 1:
+        q = q.contiguous()
+    cand = cand.contiguous()
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.b200knn_rescore_workspace_bytes(B, k_in))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        with _Timed("rescore"):
+            rc = lib.b200knn_rescore_scatter(q.data_ptr(), q.stride(0), rows_a.data_ptr(), N, D, cand.data_ptr(),
+                                             B, k_in, idx_offset, _ptr_array(peer_ptrs), len(peer_ptrs), rank,
+                                             rows_per_owner, ws.data_ptr(), ws_bytes, _stream())
+        _lib.check(rc, "rescore_scatter")
+
+
+def compact_rows(packed: torch.Tensor, col: int, mask: int, cap: int):
+    """(rows int64 (cap,), count int32 (1,)): ascending numbers of the rows of `packed` (n, ld) int64
+    whose column `col` has a bit of `mask` set, zero-padded; count may exceed cap (overflow)."""
+    n, ld = packed.shape
+    assert packed.dtype == torch.int64 and packed.stride(1) == 1
+    rows = torch.empty((cap,), dtype=torch.int64, device=packed.device)
+    count = torch.empty((1,), dtype=torch.int32, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _lib.check(_lib.load().b200knn_compact_rows(packed.data_ptr() + 8 * col, packed.stride(0), n, mask,
+                                                    rows.data_ptr(), cap, count.data_ptr(), _stream()),
+                   "compact_rows")
+    return rows, count
+
+
+def scatter_rows(dst: torch.Tensor, src: torch.Tensor, rows: torch.Tensor, count: torch.Tensor) -> None:
+    """dst[rows[i]] = src[i] for i < min(len(rows), count) — (n, w) int64 row-major tensors."""
+    assert dst.dtype == torch.int64 and src.dtype == torch.int64 and dst.stride(1) == 1 and src.stride(1) == 1
+    assert dst.shape[1] == src.shape[1] and src.shape[0] == rows.numel()
+    with torch.cuda.device(dst.device):
+        _lib.check(_lib.load().b200knn_scatter_rows(dst.data_ptr(), dst.stride(0), src.data_ptr(), src.stride(0),
+                                                    rows.data_ptr(), rows.numel(), count.data_ptr(), dst.shape[1],
+                                                    _stream()), "scatter_rows")
+
+
+def local_exact_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
+                     idx_offset: int) -> torch.Tensor:
+    """(B, k+1) int64, nothing synchronises: columns [0, k) the exact top-min(k, N) keys of this bank
+    (zero-padded) from the SECOND level of `mode`'s cascade (the last one if it has only one),
+    column k = 1 where that level's certificate failed."""
+    B = feature.shape[0]
+    N = feature_bank.shape[1]
+    levels = _cascade_levels(feature_bank, mode, track=False)
+    level = levels[1] if len(levels) > 1 else levels[0]
+    k_loc = min(int(k), N)
+    out = torch.zeros((B, k + 1), dtype=torch.int64, device=feature.device)
+    if B and k_loc:
+        keys, flags, _ = _rescored_level(feature, feature_bank, k_loc, level, idx_offset)
+        out[:, :k_loc] = keys
+        out[:, k] = flags
+    return out
+
+
 def certify(exact: torch.Tensor, approx: torch.Tensor, feature: torch.Tensor, level: dict,
             max_norm: torch.Tensor, all_rows: bool) -> torch.Tensor:
     """(n,) int32 flags: 1 where the exact k-th key does not beat the approximate k_in-th by the
@@ -736,12 +909,15 @@ def bank_max_norm(feature_bank: torch.Tensor, cand_mode: str) -> torch.Tensor:
     return bank_cache.get(feature_bank, cand_mode).max_norm()
 
 
-def _cascade_levels(feature_bank: torch.Tensor, mode: str):
+def _cascade_levels(feature_bank: torch.Tensor, mode: str, track: bool = True):
+    """track=False (sharded driver): the fixed level list of the mode — the per-process "skip the
+    first level" statistics are neither read nor decremented, so every rank of a process group
+    derives the same list (ranks that disagreed would mismatch their collectives)."""
     levels = list(CASCADES[mode])
     if len(levels) > 1 and padded_dim(feature_bank.shape[0]) > MAX_BF16_DIM:
         # no resident query tile at this width: start at the split-BF16 level
         levels = [lv for lv in levels if LEVELS[lv]["cand"] not in ("f16", "f16x2")]
-    if len(levels) > 1:
+    if len(levels) > 1 and track:
         st = bank_cache.state(feature_bank)
         if st.get("skip_first", 0) > 0:
             st["skip_first"] -= 1
@@ -755,24 +931,28 @@ def _cascade_fix(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, leve
     sub = feature[rows].contiguous()
     for level in levels:
         out, flags, n_bad = _rescored_level(sub, feature_bank, k, level, idx_offset)
+        last_rescore_stats["levels"].append((level, int(rows.numel()), int(n_bad.item())))
         if int(n_bad.item()) == 0:
             return out
         left = flags.nonzero(as_tuple=False).view(-1)
         out[left] = _cascade_fix(sub, feature_bank, k, levels[levels.index(level) + 1:], left, idx_offset)
         return out
+    last_rescore_stats["levels"].append(("exact", int(rows.numel()), 0))
     return topk_keys(sub, feature_bank, k, "exact", idx_offset)
 
 
-def _note_first_level(feature_bank: torch.Tensor, mode: str, levels, rows: int, uncertified: int) -> None:
+def _note_first_level(feature_bank: torch.Tensor, mode: str, levels, rows: int, uncertified: int,
+                      track: bool = True) -> None:
     last_rescore_stats["rows"], last_rescore_stats["uncertified"] = rows, uncertified
     last_rescore_stats["level"] = levels[0]
-    if len(CASCADES[mode]) > 1 and levels[0] == CASCADES[mode][0] and rows > 0 \
+    last_rescore_stats["levels"] = [(levels[0], rows, uncertified)]  # (level, rows in, rows left uncertified)
+    if track and len(CASCADES[mode]) > 1 and levels[0] == CASCADES[mode][0] and rows > 0 \
             and uncertified > CASCADE_GIVE_UP * rows:
         bank_cache.state(feature_bank)["skip_first"] = CASCADE_RETRY_CALLS
 
 
 def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
-                        idx_offset: int = 0, defer: bool = False):
+                        idx_offset: int = 0, defer: bool = False, track: bool = True):
     """Tensor-core candidates -> exact sequential-fma re-scoring -> best k, with a per-row
     certificate; rows a level cannot certify go to the next level and finally to the "exact"
     kernel, so the keys are bitwise those of mode "exact".
@@ -788,11 +968,11 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
     if B == 0:
         out = torch.empty((B, k), dtype=torch.int64, device=dev)
         return (out, None, None, None) if defer else out
-    levels = _cascade_levels(feature_bank, mode)
+    levels = _cascade_levels(feature_bank, mode, track)
     out, flags, n_bad = _rescored_level(feature, feature_bank, k, levels[0], idx_offset)
 
     def fix(rows, n_rows_bad):
-        _note_first_level(feature_bank, mode, levels, B, n_rows_bad)
+        _note_first_level(feature_bank, mode, levels, B, n_rows_bad, track)
         if rows is None:
             return None
         return _cascade_fix(feature, feature_bank, k, levels[1:], rows, idx_offset)
@@ -804,7 +984,7 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
         rows = flags.nonzero(as_tuple=False).view(-1)
         out[rows] = fix(rows, bad)
     else:
-        _note_first_level(feature_bank, mode, levels, B, 0)
+        _note_first_level(feature_bank, mode, levels, B, 0, track)
     return out
 
 
@@ -870,6 +1050,114 @@ def vote(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn
 # ----------------------------------------------------------------------------
 # the reference's public symbols for this path
 # ----------------------------------------------------------------------------
+def _predict_enqueue(feature, feature_bank, feature_labels, num_classes, knn_k, knn_t, mode, track=True):
+    """Everything of one tensor-core-mode call, enqueued without a host synchronisation (so it can
+    be captured into a CUDA graph): (pred (B,C), status int32[2] = [vote flag, rows to recompute],
+    bad_rows (B,) mask/flags, fix).  status[0]: 1 label / 2 neighbour index out of range;
+    status[1]: rows a sampled threshold starved, or rows whose re-scoring could not be certified."""
+    if mode in RESCORED_MODES:
+        keys, bad_rows, n_bad, fix = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True,
+                                                         track=track)
+    else:
+        keys = topk_keys(feature, feature_bank, knn_k, mode, repair=False)
+        bad_rows = keys[:, -1] == 0
+        n_bad = bad_rows.sum().to(torch.int32).view(1)
+        fix = None
+    pred, flag = vote(keys, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
+    status = torch.stack([flag.view(()), n_bad.view(()).to(torch.int32)])
+    return pred, status, bad_rows, fix
+
+
+def _predict_finish(pred, status, bad_rows, fix, feature, feature_bank, feature_labels, num_classes, knn_k,
+                    knn_t, mode):
+    """The host side of a call after its one synchronisation (`status` is a host list here)."""
+    n_fix = int(status[1])
+    if mode not in RESCORED_MODES:
+        last_prepass_stats["rows"], last_prepass_stats["repaired"] = pred.shape[0], n_fix
+    elif n_fix == 0:
+        fix(None, 0)  # records the statistics of a fully certified call
+    if n_fix:
+        rows = bad_rows.nonzero(as_tuple=False).view(-1)
+        fixed = fix(rows, n_fix) if mode in RESCORED_MODES else \
+            recompute_rows(feature, feature_bank, knn_k, mode, rows)
+        pred[rows], flag2 = vote(fixed, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
+        status[0] = max(int(status[0]), int(flag2.item()))
+    if status[0] == 1:
+        # the reference raises here from zeros(...).scatter(...) (lightly knn_predict)
+        raise RuntimeError("index out of bounds: a feature_labels entry is outside "
+                           f"[0, num_classes={int(num_classes)})")
+    if status[0] == 2:
+        raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
+    return pred
+
+
+# ---- the reference-shaped call (B = 64 per validation_step, knn.py:87-99; scripts/WM811k_benchmark.py:71)
+# is launch-latency bound: a dozen small kernels and as many Python -> C transitions per call.  For
+# batches of at most GRAPH_MAX_BATCH rows the enqueued part of a call is captured ONCE per
+# (bank, batch shape, k, C, t, mode) into a CUDA graph and replayed: one copy of the queries into
+# the graph's static input, one graph launch, one read of the status word.  A non-zero status (rows
+# to recompute, label errors — rare) re-runs the call on the ordinary path, so results and errors
+# are exactly those of the un-captured call.
+GRAPH_MAX_BATCH = 512
+GRAPHS = {"enabled": os.environ.get("B200KNN_GRAPHS", "1") == "1", "capacity": 4}
+graph_stats = {"captures": 0, "replays": 0, "fallbacks": 0}
+
+
+class _CallGraph:
+    __slots__ = ("graph", "q_static", "pred", "status_host", "bad_rows", "fix", "bank_ref", "keep")
+
+
+_call_graphs = {}
+
+
+def _graph_key(feature, feature_bank, labels, num_classes, knn_k, knn_t, mode):
+    return (feature_bank.data_ptr(), feature_bank._version, tuple(feature_bank.shape), tuple(feature_bank.stride()),
+            feature_bank.dtype, feature_bank.device.index, labels.data_ptr(), labels._version,
+            tuple(feature.shape), feature.dtype, int(num_classes), int(knn_k), float(knn_t), mode)
+
+
+def _graph_for(feature, feature_bank, labels, num_classes, knn_k, knn_t, mode):
+    for dead in [k_ for k_, g in _call_graphs.items() if g.bank_ref() is None]:
+        _call_graphs.pop(dead)
+    key = _graph_key(feature, feature_bank, labels, num_classes, knn_k, knn_t, mode)
+    hit = _call_graphs.get(key)
+    if hit is not None:
+        return hit
+    dev = feature.device
+    entry = _CallGraph()
+    entry.q_static = torch.empty_like(feature, memory_format=torch.contiguous_format)
+    entry.q_static.copy_(feature)
+    entry.status_host = torch.zeros((2,), dtype=torch.int32).pin_memory()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up on a side stream, as graph capture requires
+        query_cache.clear()
+        _predict_enqueue(entry.q_static, feature_bank, labels, num_classes, knn_k, knn_t, mode, track=False)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize(dev)
+    query_cache.clear()
+    entry.graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(entry.graph):
+        pred, status, bad_rows, fix = _predict_enqueue(entry.q_static, feature_bank, labels, num_classes, knn_k,
+                                                       knn_t, mode, track=False)
+        entry.status_host.copy_(status, non_blocking=True)
+    query_cache.clear()  # it now refers to tensors of the graph's private pool
+    entry.pred, entry.bad_rows, entry.fix = pred, bad_rows, fix
+    entry.bank_ref = weakref.ref(feature_bank)
+    # the graph holds raw pointers into the prepared copies of this bank (operands, re-scoring rows,
+    # max norm) and into the labels: keep them alive for as long as the graph
+    entry.keep = [labels] + [prep for ref, prep in bank_cache._entries.values() if ref() is feature_bank]
+    if len(_call_graphs) >= GRAPHS["capacity"]:
+        _call_graphs.pop(next(iter(_call_graphs)))
+    _call_graphs[key] = entry
+    graph_stats["captures"] += 1
+    return entry
+
+
+def clear_call_graphs() -> None:
+    _call_graphs.clear()
+
+
 def knn_predict(feature: torch.Tensor, feature_bank: torch.Tensor, feature_labels: torch.Tensor,
                 num_classes: int, knn_k: int = 200, knn_t: float = 0.1) -> torch.Tensor:
     """Drop-in for ``lightly.utils.benchmarking.knn_predict`` (reference call sites
@@ -886,42 +1174,38 @@ def knn_predict(feature: torch.Tensor, feature_bank: torch.Tensor, feature_label
         _check_feature_bank(feature, feature_bank)
         raise RuntimeError(
             f"feature_labels has {feature_labels.numel()} entries for a bank of {feature_bank.shape[1]}")
-    if mode == "exact":
+    if mode == "exact" or int(knn_k) > MAX_K:
         return vote(topk_keys(feature, feature_bank, knn_k, mode), feature_labels, num_classes, knn_t)
+    _check_feature_bank(feature, feature_bank)
+    knn_k = int(knn_k)
+    if knn_k <= 0 or knn_k > feature_bank.shape[1]:
+        raise RuntimeError("selected index k out of range")
+    if feature.shape[0] == 0:
+        return vote(torch.empty((0, knn_k), dtype=torch.int64, device=feature.device), feature_labels,
+                    num_classes, knn_t)
     # Tensor-core modes: everything is enqueued first and ONE host synchronisation reads the
-    # status word: bit 0/1 vote flag (label / index out of range), bit 2 rows to recompute (rows a
-    # sampled threshold starved, or rows whose exact re-scoring could not be certified).
-    dev = feature.device
-    if mode in RESCORED_MODES:
-        keys, bad_rows, n_bad, fix = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True)
-        if n_bad is None:  # B == 0
-            return vote(keys, feature_labels, num_classes, knn_t)
-    else:
-        keys = topk_keys(feature, feature_bank, knn_k, mode, repair=False)
-        if keys.shape[0] == 0:
-            return vote(keys, feature_labels, num_classes, knn_t)
-        bad_rows = keys[:, -1] == 0
-        n_bad = bad_rows.sum().to(torch.int32).view(1)
-    pred, flag = vote(keys, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
-    status = torch.stack([flag.view(()), n_bad.view(()).to(torch.int32)]).tolist()
-    n_fix = int(status[1])
-    if mode not in RESCORED_MODES:
-        last_prepass_stats["rows"], last_prepass_stats["repaired"] = keys.shape[0], n_fix
-    elif n_fix == 0:
-        fix(None, 0)  # records the statistics of a fully certified call
-    if n_fix:
-        rows = bad_rows.nonzero(as_tuple=False).view(-1)
-        fixed = fix(rows, n_fix) if mode in RESCORED_MODES else \
-            recompute_rows(feature, feature_bank, knn_k, mode, rows)
-        pred[rows], flag2 = vote(fixed, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
-        status[0] = max(int(status[0]), int(flag2.item()))
-    if status[0] == 1:
-        # the reference raises here from zeros(...).scatter(...) (lightly knn_predict)
-        raise RuntimeError("index out of bounds: a feature_labels entry is outside "
-                           f"[0, num_classes={int(num_classes)})")
-    if status[0] == 2:
-        raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
-    return pred
+    # status word (vote flag; rows to recompute: rows a sampled threshold starved, or rows whose
+    # exact re-scoring could not be certified).
+    if GRAPHS["enabled"] and feature.shape[0] <= GRAPH_MAX_BATCH and feature_labels.dtype == torch.int64 \
+            and feature_labels.is_contiguous() and not torch.cuda.is_current_stream_capturing():
+        with torch.cuda.device(feature.device):
+            g = _graph_for(feature, feature_bank, feature_labels, num_classes, knn_k, knn_t, mode)
+            g.q_static.copy_(feature)
+            g.graph.replay()
+            pred = g.pred.clone()
+            torch.cuda.current_stream().synchronize()
+            graph_stats["replays"] += 1
+            if not g.status_host.any():
+                return pred
+            # rows to recompute / label errors: the ordinary host side, on the graph's own buffers
+            # (q_static still holds this call's queries)
+            graph_stats["fallbacks"] += 1
+            return _predict_finish(pred, g.status_host.tolist(), g.bad_rows, g.fix, g.q_static, feature_bank,
+                                   feature_labels, num_classes, knn_k, knn_t, mode)
+    pred, status, bad_rows, fix = _predict_enqueue(feature, feature_bank, feature_labels, num_classes, knn_k,
+                                                   knn_t, mode)
+    return _predict_finish(pred, status.tolist(), bad_rows, fix, feature, feature_bank, feature_labels,
+                           num_classes, knn_k, knn_t, mode)
 
 
 def knn_topk(feature: torch.Tensor, feature_bank: torch.Tensor, k: int,

@@ -29,6 +29,7 @@ import torch
 import torch.distributed as dist
 
 _TC_MODES = ("bf16", "tf32x3", "bf16x3", "f16x2", "f16")  # = knn.TC_MODES (raw tensor-core similarity modes)
+_MAX_K = 992  # = knn.MAX_K (largest k of the streaming candidate lists)
 
 
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -127,6 +128,32 @@ class _CudaOps:
         from .knn import bank_max_norm
         return bank_max_norm(bank_shard, cand_mode)
 
+    # ---- the same exchange over NVLink peer memory, and the device-side hand-over between levels
+    @staticmethod
+    def route_scatter(keys, rows_per_shard, n_shards, inbox_ptrs, row_offset):
+        from .knn import route_scatter
+        return route_scatter(keys, rows_per_shard, n_shards, inbox_ptrs, row_offset)
+
+    @staticmethod
+    def rescore_scatter(feature, bank_shard, cand, cand_mode, idx_offset, peer_ptrs, rank, rows_per_owner):
+        from .knn import rescore_scatter
+        return rescore_scatter(feature, bank_shard, cand, cand_mode, idx_offset, peer_ptrs, rank, rows_per_owner)
+
+    @staticmethod
+    def compact_rows(packed, col, mask, cap):
+        from .knn import compact_rows
+        return compact_rows(packed, col, mask, cap)
+
+    @staticmethod
+    def scatter_rows(dst, src, rows, count):
+        from .knn import scatter_rows
+        return scatter_rows(dst, src, rows, count)
+
+    @staticmethod
+    def local_exact_keys(feature, bank_shard, k, mode, idx_offset):
+        from .knn import local_exact_keys
+        return local_exact_keys(feature, bank_shard, k, mode, idx_offset)
+
 
 class ShardedBank:
     """A (D, N) bank whose columns (bank rows) are partitioned over a process group.
@@ -224,53 +251,6 @@ class ShardedBank:
                 merged[rows] = self.ops.merge_keys(self._gather(self.local_keys(sub, k, None)), k)
         return merged
 
-    def _predict_level(self, feature, C, knn_k, knn_t, level):
-        """One cascade level for the given (replicated) query rows: ((n, C) rankings, (n,) status)
-        identical on every rank.  Status bits: 0 starved, 1 / 2 label / index out of range, 3 uncertified."""
-        n = feature.shape[0]
-        per, lo, hi = self._owned(n)
-        merged, flags = self._owned_keys_rescored(feature, knn_k, level)
-        packed = self.ops.vote_packed(merged[:hi - lo], self.labels, C, knn_t, per)
-        packed[:hi - lo, C] |= flags.to(torch.int64) << 3
-        gathered = torch.empty((per * self.world_size, C + 1), dtype=torch.int64, device=feature.device)
-        dist.all_gather_into_tensor(gathered, packed, group=self.group)
-        self._mark("vote+gather")
-        return gathered[:n, :C].contiguous(), gathered[:n, C].contiguous()
-
-    def _knn_predict_rescored(self, feature, C, knn_k, knn_t, levels) -> torch.Tensor:
-        self._mark("start")
-        out, status = self._predict_level(feature, C, knn_k, knn_t, levels[0])
-        worst = int(status.max().item())  # the one host synchronisation of a fully certified call
-        self.last_uncertified = 0
-        # Rows a level could not certify (or a sampled threshold starved) go to the next level; the
-        # status words are identical on every rank, so every rank takes the same branches and the
-        # collectives stay matched.
-        for level in levels[1:2]:
-            if not worst & 9:
-                break
-            rows = ((status & 9) != 0).nonzero(as_tuple=False).view(-1)
-            self.last_uncertified = max(self.last_uncertified, int(rows.numel()))
-            o2, s2 = self._predict_level(feature[rows].contiguous(), C, knn_k, knn_t, level)
-            out[rows] = o2
-            status[rows] = s2
-            worst = int(status.max().item())
-        if worst & 9:
-            rows = ((status & 9) != 0).nonzero(as_tuple=False).view(-1)
-            self.last_uncertified = max(self.last_uncertified, int(rows.numel()))
-            sub = feature[rows].contiguous()
-            # per-shard exact top-k through the single-GPU cascade, all-gathered and merged
-            keys = self.ops.merge_keys(self._gather(self.local_keys(sub, knn_k, None)), knn_k)
-            pk = self.ops.vote_packed(keys, self.labels, C, knn_t, rows.numel())
-            out[rows] = pk[:, :C]
-            status[rows] = pk[:, C]
-            worst = int(status.max().item())
-        if worst & 2:
-            raise RuntimeError("index out of bounds: a feature_labels entry is outside "
-                               f"[0, num_classes={C})")
-        if worst & 4:
-            raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
-        return out
-
     last_uncertified = 0
 
     def knn_topk(self, feature: torch.Tensor, k: int):
@@ -302,42 +282,64 @@ class ShardedBank:
     # ------------------------------------------------------------------ fused exchange (NVLink P2P)
     fused_exchange = os.environ.get("B200KNN_FUSED_EXCHANGE", "1") == "1"
 
-    def _symmetric_buffer(self, per: int, k: int, device):
-        """(G, per, k) int64 exchange buffer in symmetric memory + its rendezvous handle (every
-        rank's copy is mapped into every process: handle.buffer_ptrs), cached per shape."""
-        key = (per, k)
-        hit = self._symm.get(key)
-        if hit is None:
-            import torch.distributed._symmetric_memory as symm_mem
+    def _symmetric_regions(self, n_regions: int, per: int, k: int, device):
+        """n_regions exchange buffers of shape (G, per, k) int64 carved out of ONE symmetric-memory
+        allocation (every rank's copy is mapped into every process), plus the rendezvous handle and
+        per region the list of all ranks' device pointers to it.  Allocations are bucketed by size
+        (powers of two) and shared by every call shape that fits, so a new batch size or a new
+        count of uncertified rows does not trigger a new allocation + rendezvous collective.
+        Returns (regions, handle, ptrs, fresh): fresh is True when the layout differs from the
+        previous call's, i.e. rows a kernel never writes may hold another layout's keys."""
+        import torch.distributed._symmetric_memory as symm_mem
 
-            buf = symm_mem.empty((self.world_size, per, k), dtype=torch.int64, device=device)
-            buf.zero_()  # rows past B are never written: they must read as empty lists
-            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-            hit = self._symm[key] = (buf, hdl)
-        return hit
+        G = self.world_size
+        need = n_regions * G * per * k
+        bucket = 1 << max(20, (need - 1).bit_length())
+        hit = self._symm.get(("buf", bucket))
+        if hit is None:
+            for key in [key for key in self._symm if key[0] == "buf" and key[1] < bucket]:
+                self._symm.pop(key)  # superseded by the larger allocation
+            flat = symm_mem.empty((bucket,), dtype=torch.int64, device=device)
+            flat.zero_()
+            hdl = symm_mem.rendezvous(flat, self.group if self.group is not None else dist.group.WORLD)
+            hit = self._symm[("buf", bucket)] = [flat, hdl, None]
+        flat, hdl, layout = hit
+        fresh = layout != (n_regions, per, k)
+        hit[2] = (n_regions, per, k)
+        size = G * per * k
+        regions = [flat[r * size:(r + 1) * size].view(G, per, k) for r in range(n_regions)]
+        ptrs = [[int(base) + r * size * 8 for base in hdl.buffer_ptrs] for r in range(n_regions)]
+        return regions, hdl, ptrs, fresh
+
+    def _fused_ok(self, feature: torch.Tensor, k: int, mode: str) -> bool:
+        """Whether the fused (peer-memory) exchange applies — decided from quantities every rank
+        knows, so the decision is the same everywhere."""
+        if not (self.fused_exchange and feature.is_cuda and hasattr(self.ops, "topk_scatter")):
+            return False
+        if self.world_size > 8 or mode not in _TC_MODES:
+            return False
+        B, D = feature.shape
+        for r in range(self.world_size):
+            lo, hi = shard_bounds(self.n_rows, self.world_size, r)
+            if hi - lo < k or not self.ops.scatter_supported(B, hi - lo, D, k, mode):
+                return False
+        return True
 
     def _owned_keys_fused(self, feature: torch.Tensor, k: int, tau0, per: int) -> Optional[torch.Tensor]:
         """The compute step and its collective as ONE kernel: every shard's tc_topk kernel stores the
         keys of each query tile it finishes into the owner GPU's exchange buffer over NVLink, so the
         all-to-all overlaps the remaining tiles' math.  Returns None when not applicable."""
-        if not (self.fused_exchange and feature.is_cuda and hasattr(self.ops, "topk_scatter")):
+        if not self._fused_ok(feature, k, self.mode):
             return None
-        if self.world_size > 8 or self.mode not in _TC_MODES:
-            return None
-        # the decision must be the same on every rank: check every shard's size and work plan
-        B, D = feature.shape
-        for r in range(self.world_size):
-            lo, hi = shard_bounds(self.n_rows, self.world_size, r)
-            if hi - lo < k or not self.ops.scatter_supported(B, hi - lo, D, k, self.mode):
-                return None
         try:
-            buf, hdl = self._symmetric_buffer(per, k, feature.device)
+            (buf,), hdl, (ptrs,), fresh = self._symmetric_regions(1, per, k, feature.device)
         except Exception:  # symmetric memory unavailable on this system: NCCL exchange instead
             type(self).fused_exchange = False
             return None
+        if fresh:
+            buf.zero_()  # rows past B are never written: they must read as empty lists
         hdl.barrier(channel=0)  # every rank is done reading its buffer of the previous call
-        ok = self.ops.topk_scatter(feature, self.bank_shard, k, self.mode, self.lo, tau0,
-                                   list(hdl.buffer_ptrs), self.rank, per)
+        ok = self.ops.topk_scatter(feature, self.bank_shard, k, self.mode, self.lo, tau0, ptrs, self.rank, per)
         self._mark("  local topk + scatter")
         hdl.barrier(channel=1)  # every rank's stores have landed
         if not ok:
@@ -388,36 +390,147 @@ class ShardedBank:
         1. every shard's tensor-core candidates (k + margin, under one global sampled threshold) go
            to the owner of the query (fused scatter / all-to-all) and are merged there: the global
            approximate top-(k + margin), exactly what one GPU would have produced;
-        2. the owner routes each candidate to the shard that holds its bank row (all-to-all), that
-           shard re-scores it exactly (sequential fma) and returns the exact key (all-to-all);
+        2. the owner routes each candidate to the shard that holds its bank row, that shard
+           re-scores it exactly (sequential fma) and returns the exact key;
         3. the owner merges the exact keys and evaluates the single-GPU certificate.
+        Steps 2-3 run over NVLink peer memory when the fused exchange applies (route_scatter ->
+        rescore_scatter, four symmetric-memory barriers, no NCCL call), else as two all-to-alls.
         Returns (exact keys (per, k), uncertified flags (n_owned,) int32) for the owned query rows."""
         import copy
         B = feature.shape[0]
         per, lo, hi = self._owned(B)
         G = self.world_size
-        k_in = min(k + level["margin"], self.n_rows)
+        # the streaming lists hold MAX_K keys: near that limit the margin shrinks (as on one GPU)
+        k_in = min(k + level["margin"], self.n_rows, max(k, _MAX_K))
         cand = copy.copy(self)  # same shard, buffers and phase log; candidate mode instead of "fp32"
         cand.mode = level["cand"]
         tau0 = cand.global_threshold(feature, k_in)
         self._mark("threshold")
-        approx = cand.owned_keys(feature, k_in, tau0)                  # (per, k_in)
-        self._mark("candidates+exchange+merge")
         rows_per_shard = (self.n_rows + G - 1) // G
-        routed = self.ops.route_keys(approx, rows_per_shard, G)       # (G, per, k_in)
-        mine = self._exchange_owned(routed.view(G * per, k_in), per)   # (G, per, k_in): all queries, my rows
-        self._mark("  route + all-to-all")
-        exact_local = torch.zeros((G * per, k_in), dtype=torch.int64, device=feature.device)
-        if B:
-            exact_local[:B] = self.ops.rescore_sparse(feature, self.bank_shard, mine.view(G * per, k_in)[:B],
-                                                      level["cand"], self.lo)
-        self._mark("  re-score")
-        back = self._exchange_owned(exact_local, per)                  # (G, per, k_in): my queries, every shard
-        merged = self.ops.merge_keys(back, k)                          # (per, k) exact
-        flags = self.ops.certify(merged[:hi - lo], approx[:hi - lo], feature[lo:hi], level,
-                                 self._global_max_norm(level["cand"]), k_in >= self.n_rows)
-        self._mark("  all-to-all + merge + certify")
+        max_norm = self._global_max_norm(level["cand"])
+        fused = B > 0 and hasattr(self.ops, "rescore_scatter") and self._fused_ok(feature, k_in, level["cand"])
+        if fused:
+            try:
+                (exch1, inbox, exch2), hdl, (p1, p_in, p2), fresh = \
+                    self._symmetric_regions(3, per, k_in, feature.device)
+            except Exception:
+                type(self).fused_exchange = False
+                fused = False
+        if fused:
+            if fresh:
+                exch1.zero_()
+            inbox.zero_()   # written sparsely by the peers (non-empty prefixes only)
+            exch2.zero_()
+            hdl.barrier(channel=0)  # every rank has zeroed its buffers and is done with the previous call
+            if not self.ops.topk_scatter(feature, self.bank_shard, k_in, level["cand"], self.lo, tau0, p1,
+                                         self.rank, per):
+                raise RuntimeError("b200knn: fused exchange refused after the collective decision to use it")
+            self._mark("  candidates + scatter")
+            hdl.barrier(channel=1)
+            approx = self.ops.merge_keys(exch1, k_in)                     # (per, k_in) global approximate top
+            self.ops.route_scatter(approx[:hi - lo], rows_per_shard, G, p_in, self.rank * per)
+            self._mark("  merge + route")
+            hdl.barrier(channel=2)
+            # my bank rows among the candidates of ALL queries -> exact keys -> each query's owner
+            self.ops.rescore_scatter(feature, self.bank_shard, inbox.view(G * per, k_in)[:B], level["cand"],
+                                     self.lo, p2, self.rank, per)
+            self._mark("  re-score + scatter")
+            hdl.barrier(channel=3)
+            merged = self.ops.merge_keys(exch2, k)                        # (per, k) exact
+        else:
+            approx = cand.owned_keys(feature, k_in, tau0)                  # (per, k_in)
+            self._mark("candidates+exchange+merge")
+            routed = self.ops.route_keys(approx, rows_per_shard, G)       # (G, per, k_in)
+            mine = self._exchange_owned(routed.view(G * per, k_in), per)   # (G, per, k_in): all queries, my rows
+            self._mark("  route + all-to-all")
+            exact_local = torch.zeros((G * per, k_in), dtype=torch.int64, device=feature.device)
+            if B:
+                exact_local[:B] = self.ops.rescore_sparse(feature, self.bank_shard, mine.view(G * per, k_in)[:B],
+                                                          level["cand"], self.lo)
+            self._mark("  re-score")
+            back = self._exchange_owned(exact_local, per)                  # (G, per, k_in): my queries, every shard
+            merged = self.ops.merge_keys(back, k)                          # (per, k) exact
+        flags = self.ops.certify(merged[:hi - lo], approx[:hi - lo], feature[lo:hi], level, max_norm,
+                                 k_in >= self.n_rows)
+        self._mark("  merge + certify")
         return merged, flags
+
+    def _predict_level_packed(self, feature, C, knn_k, knn_t, level):
+        """One cascade level for all (replicated) query rows: (G*per, C+1) int64, identical on every
+        rank — class rankings in columns [0, C), status word in column C (bit 0 starved row, bits
+        1 / 2 label / index out of range, bit 3 uncertified)."""
+        n = feature.shape[0]
+        per, lo, hi = self._owned(n)
+        merged, flags = self._owned_keys_rescored(feature, knn_k, level)
+        packed = self.ops.vote_packed(merged[:hi - lo], self.labels, C, knn_t, per)
+        packed[:hi - lo, C] |= flags.to(torch.int64) << 3
+        gathered = torch.empty((per * self.world_size, C + 1), dtype=torch.int64, device=feature.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        self._mark("vote+gather")
+        return gathered
+
+    # capacity of the device-side second level, per batch size (doubles after an overflow; every
+    # rank sees the same counts, so every rank keeps the same value)
+    _l2_cap = None
+
+    def _knn_predict_rescored(self, feature, C, knn_k, knn_t, levels) -> torch.Tensor:
+        """Sharded fp32 mode, ONE host synchronisation per call.
+        Level 1 (all rows): `_owned_keys_rescored` at the cascade's first level.  Rows it leaves
+        uncertified or starved (status bits 3 / 0 — identical on every rank after the all-gather)
+        are compacted ON THE DEVICE into a fixed-capacity sub-batch; level 2 recomputes that
+        sub-batch exactly on every shard's own rows (single-GPU cascade level 2: fp16 x split-fp16
+        candidates + exact re-scoring + the shard-local certificate — a shard holds 1/G of the bank,
+        so its rank gaps are G times wider), the per-shard exact top-k are all-gathered and merged
+        and the rankings scattered back.  Only then is one status word read; rows still open (level 2
+        uncertified on some shard, or more open rows than the capacity) take the host-driven path."""
+        B = feature.shape[0]
+        self._mark("start")
+        packed = self._predict_level_packed(feature, C, knn_k, knn_t, levels[0])
+        out = packed[:B]
+        n_open = None
+        if hasattr(self.ops, "compact_rows"):
+            if self._l2_cap is None:
+                self._l2_cap = {}
+            cap = self._l2_cap.get(B) or min(B, max(256, -(-B // 64)))
+            rows, count = self.ops.compact_rows(out, C, 9, cap)
+            sub = feature.index_select(0, rows)
+            loc = self.ops.local_exact_keys(sub, self.bank_shard, knn_k, self.mode, self.lo)   # (cap, k+1)
+            allk = self._gather(loc)                                                        # (G, cap, k+1)
+            keys2 = self.ops.merge_keys(allk[:, :, :knn_k].contiguous(), knn_k)
+            pk2 = self.ops.vote_packed(keys2, self.labels, C, knn_t, cap)
+            pk2[:, C] |= (allk[:, :, knn_k].amax(0) != 0).to(torch.int64) << 3
+            self.ops.scatter_rows(out, pk2, rows, count)
+            n_open = count
+            self._mark("level 2 (open rows, per shard)")
+        # one host read: OR of the status bits over all rows + the number of rows level 1 left open
+        shifts = torch.arange(4, device=out.device)
+        bits = ((out[:, C:C + 1] >> shifts) & 1).amax(0)
+        if n_open is None:
+            host = bits.tolist() + [0]
+        else:
+            host = torch.cat([bits, n_open.view(1).to(bits.dtype)]).tolist()
+        status = out[:, C]
+        pred = out[:, :C].contiguous()
+        self.last_uncertified = int(host[4]) if n_open is not None else int(((status & 9) != 0).sum().item())
+        if n_open is not None and host[4] > cap:
+            self._l2_cap[B] = min(B, 2 * max(cap, int(host[4])))
+        if host[0] or host[3]:
+            # host-driven path (identical status on every rank -> matched collectives): per-shard
+            # exact top-k through the single-GPU cascade, all-gathered and merged
+            rows = ((status & 9) != 0).nonzero(as_tuple=False).view(-1)
+            sub = feature[rows].contiguous()
+            keys = self.ops.merge_keys(self._gather(self.local_keys(sub, knn_k, None)), knn_k)
+            pk = self.ops.vote_packed(keys, self.labels, C, knn_t, rows.numel())
+            pred[rows] = pk[:, :C]
+            worst = int(pk[:, C].max().item()) if rows.numel() else 0
+            host[1] = host[1] or (worst & 2)
+            host[2] = host[2] or (worst & 4)
+        if host[1]:
+            raise RuntimeError("index out of bounds: a feature_labels entry is outside "
+                               f"[0, num_classes={C})")
+        if host[2]:
+            raise RuntimeError("index out of bounds: neighbour index outside feature_labels")
+        return pred
 
     def knn_predict(self, feature: torch.Tensor, num_classes: int, knn_k: int = 200,
                     knn_t: float = 0.1, exchange: str = "alltoall") -> torch.Tensor:

@@ -43,7 +43,7 @@ bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan*
     *plan = b200knn::make_plan(B, N, k, cap, 128, 128, sms * 2);
   } else {
     // a worker of the tensor-core kernel is one CTA, or a CTA pair owning 256 query rows
-    const int pair = b200knn::tc_use_pair(mode) ? 2 : 1;
+    const int pair = b200knn::tc_use_pair(mode, B) ? 2 : 1;
     *plan = b200knn::make_plan(B, N, k, cap, 128 * pair, b200knn::tc_tile_n(mode, dim), sms / pair);
   }
   return true;
@@ -93,7 +93,7 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
                      float* dump, int32_t* diag, int flags, int64_t bank_row_stride = 1,
                      const float* tau0 = nullptr, bool sample = false,
                      const void* const* host_peer_out = nullptr, int n_peers = 0, int my_rank = 0,
-                     int64_t rows_per_owner = 0) {
+                     int64_t rows_per_owner = 0, const uint64_t* upper = nullptr) {
   if (B < 0 || N <= 0 || dim <= 0) return fail(B200KNN_E_ARG, "topk: bad shape");
   if (k <= 0 || k > N) return fail(B200KNN_E_ARG, "topk: selected index k out of range");
   if (N + idx_offset >= 0xFFFFFFFFll || idx_offset < 0)
@@ -140,6 +140,7 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.split_rows = plan.split_rows;
     p.lists = lists;
     p.out = partial;
+    p.upper = upper;
     e = b200knn::launch_exact(p, plan.grid, plan.cap, st);
     if (e != cudaSuccess) return fail_cuda("topk(exact)", e);
   } else if (is_tc_mode(mode)) {
@@ -194,6 +195,15 @@ int b200knn_topk(int mode, const void* q_hi, const void* q_lo, int q_dtype, int6
   return topk_impl(mode, q_hi, q_lo, q_dtype, q_ld, bank_hi, bank_lo, bank_dtype, bank_layout,
                    bank_ld, B, N, dim, k, idx_offset, out_keys, workspace, workspace_bytes, stream,
                    nullptr, nullptr, 0);
+}
+
+int b200knn_topk_exact_below(const void* q, int q_dtype, int64_t q_ld, const void* bank, int bank_dtype,
+                             int bank_layout, int64_t bank_ld, int64_t B, int64_t N, int dim, int k,
+                             int64_t idx_offset, const uint64_t* upper_keys, uint64_t* out_keys,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  return topk_impl(B200KNN_MODE_EXACT, q, nullptr, q_dtype, q_ld, bank, nullptr, bank_dtype, bank_layout,
+                   bank_ld, B, N, dim, k, idx_offset, out_keys, workspace, workspace_bytes, stream, nullptr,
+                   nullptr, 0, 1, nullptr, false, nullptr, 0, 0, 0, upper_keys);
 }
 
 int b200knn_topk_ex(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
@@ -350,6 +360,78 @@ int b200knn_route_keys(const uint64_t* keys, int64_t n, int k, int64_t rows_per_
   cudaError_t e = b200knn::launch_route_keys(keys, n, k, rows_per_shard, n_shards, out,
                                              static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? B200KNN_OK : fail_cuda("route_keys", e);
+}
+
+int b200knn_route_scatter(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int n_shards,
+                          const void* const* host_inbox, int64_t row_offset, void* stream) {
+  if (!keys || !host_inbox || n < 0 || k <= 0 || rows_per_shard <= 0 || n_shards <= 0 || n_shards > 8 ||
+      row_offset < 0)
+    return fail(B200KNN_E_ARG, "route_scatter: bad argument (1..8 shards)");
+  uint64_t* inbox[8];
+  for (int g = 0; g < n_shards; ++g) {
+    if (!host_inbox[g]) return fail(B200KNN_E_ARG, "route_scatter: null inbox");
+    inbox[g] = static_cast<uint64_t*>(const_cast<void*>(host_inbox[g]));
+  }
+  cudaError_t e = b200knn::launch_route_scatter(keys, n, k, rows_per_shard, n_shards, inbox, row_offset,
+                                                static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("route_scatter", e);
+}
+
+int b200knn_rescore_scatter(const float* q, int64_t q_ld, const float* rows, int64_t N, int dim,
+                            const uint64_t* cand_keys, int64_t B, int k_in, int64_t idx_offset,
+                            const void* const* host_peer_out, int n_peers, int my_rank,
+                            int64_t rows_per_owner, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q || !rows || !cand_keys || !host_peer_out || !workspace)
+    return fail(B200KNN_E_ARG, "rescore_scatter: null pointer");
+  if (B < 0 || N <= 0 || dim <= 0 || k_in <= 0 || k_in > 1024)
+    return fail(B200KNN_E_ARG, "rescore_scatter: bad shape (need 0 < k_in <= 1024)");
+  if (n_peers < 1 || n_peers > 8 || my_rank < 0 || my_rank >= n_peers || rows_per_owner <= 0 ||
+      rows_per_owner * n_peers < B)
+    return fail(B200KNN_E_ARG, "rescore_scatter: 1..8 peers, a rank among them, rows_per_owner * n_peers >= B");
+  if (reinterpret_cast<uintptr_t>(rows) % 16 != 0)
+    return fail(B200KNN_E_ARG, "rescore_scatter: rows must be 16-byte aligned");
+  if (workspace_bytes < b200knn::rescore_workspace_bytes(B, k_in))
+    return fail(B200KNN_E_WORKSPACE, "rescore_scatter: workspace too small");
+  b200knn::RescoreParams p = {};
+  p.q = q;
+  p.q_dtype = B200KNN_F32;
+  p.q_ld = q_ld;
+  p.rows_a = rows;
+  p.rows_b = nullptr;
+  p.dim = dim;
+  p.dim_pad = (dim + 63) / 64 * 64;
+  p.cand = cand_keys;
+  p.B = B;
+  p.k_in = k_in;
+  p.k_out = k_in;
+  p.idx_offset = idx_offset;
+  p.n_peers = n_peers;
+  p.my_rank = my_rank;
+  p.rows_per_owner = rows_per_owner;
+  for (int g = 0; g < n_peers; ++g) {
+    if (!host_peer_out[g]) return fail(B200KNN_E_ARG, "rescore_scatter: null peer buffer");
+    p.peer_out[g] = static_cast<uint64_t*>(const_cast<void*>(host_peer_out[g]));
+  }
+  cudaError_t e = b200knn::launch_rescore(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("rescore_scatter", e);
+}
+
+int b200knn_compact_rows(const int64_t* status, int64_t ld, int64_t n, int64_t mask, int64_t* rows_out,
+                         int cap, int32_t* count_out, void* stream) {
+  if (!status || !rows_out || !count_out || ld <= 0 || n < 0 || cap <= 0)
+    return fail(B200KNN_E_ARG, "compact_rows: bad argument");
+  cudaError_t e = b200knn::launch_compact_rows(status, ld, n, mask, rows_out, cap, count_out,
+                                               static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("compact_rows", e);
+}
+
+int b200knn_scatter_rows(int64_t* dst, int64_t dst_ld, const int64_t* src, int64_t src_ld,
+                         const int64_t* rows, int n, const int32_t* count, int width, void* stream) {
+  if (!dst || !src || !rows || !count || n < 0 || width < 0 || dst_ld < width || src_ld < width)
+    return fail(B200KNN_E_ARG, "scatter_rows: bad argument");
+  cudaError_t e = b200knn::launch_scatter_rows(dst, dst_ld, src, src_ld, rows, n, count, width,
+                                               static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("scatter_rows", e);
 }
 
 size_t b200knn_rescore_workspace_bytes(int64_t B, int k_in) {

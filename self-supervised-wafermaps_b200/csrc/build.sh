@@ -12,7 +12,9 @@ LIBNAME="${LIBNAME:-libb200knn.so}"
 BUILD="${BUILD_DIR:-build}"
 mkdir -p "$here/$BUILD"
 pids=()
-for f in api exact select vote prepare rescore tc_topk; do
+TC_INST="tc_inst_bf16_pair tc_inst_bf16_single tc_inst_f16_pair tc_inst_f16_single tc_inst_f16x2_pair tc_inst_f16x2_single tc_inst_bf16x3 tc_inst_tf32x3"
+SRCS="$TC_INST api exact select vote prepare rescore tc_topk sharded_ops"
+for f in $SRCS; do
   ( "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$here/$BUILD/$f.o" > "$here/$BUILD/$f.log" 2>&1 ) &
   pids+=($!)
 done
@@ -22,6 +24,7 @@ if [ $rc -ne 0 ]; then
   grep -h -E "error|Error" "$here"/$BUILD/*.log || true
   exit 1
 fi
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/$LIBNAME" \
-  "$here"/$BUILD/{api,exact,select,vote,prepare,rescore,tc_topk}.o -cudart static
+objs=()
+for f in $SRCS; do objs+=("$here/$BUILD/$f.o"); done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/$LIBNAME" "${objs[@]}" -cudart static
 echo "built $out/$LIBNAME"

@@ -165,7 +165,11 @@ __device__ __forceinline__ float warp_prune_select(uint64_t* list, int n_valid, 
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) c += (hi[r] >= T) ? 1 : 0;
   c = __reduce_add_sync(kFull, c);
-  if (c > k + (CAP - k) / 4) {
+  // Every caller may append up to 32 more keys before it checks the list again, so the kept
+  // count must also leave 32 free slots (k close to CAP: one tie at the cut would otherwise let
+  // the next chunk of appends run past the list).
+  const int room = (k + (CAP - k) / 4 < CAP - 32) ? k + (CAP - k) / 4 : CAP - 32;
+  if (c > room) {
     *kept = -1;
     return 0.0f;
   }

@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(ExactParams p) {
     RowState st;
     st.cnt = 0;
     st.tau = (m0 + tid < p.B) ? neg_inf : pos_inf;  // only meaningful for tid < TM
+    // k > 992 is served in passes ("peeling", b200knn/knn.py): pass i admits only keys strictly
+    // below the last key of pass i-1.  Filtering the stream keeps the threshold logic valid.
+    const uint64_t upper = (p.upper != nullptr && tid < TM && m0 + tid < p.B) ? p.upper[m0 + tid] : ~0ull;
 
     for (int64_t n0 = n_begin; n0 < n_end; n0 += TN) {
       float acc[8][8];
@@ -134,7 +137,8 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(ExactParams p) {
           for (int j = 0; j < 32; ++j) {
             if (s[j] > st.tau) {
               const int64_t gn = n0 + c0 + j;
-              if (gn < n_end) my_list[c++] = make_key(s[j], uint32_t(gn + p.idx_offset));
+              const uint64_t key = make_key(s[j], uint32_t(gn + p.idx_offset));
+              if (gn < n_end && key < upper) my_list[c++] = key;
             }
           }
           st.cnt = c;

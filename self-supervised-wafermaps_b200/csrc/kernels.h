@@ -20,6 +20,7 @@ struct ExactParams {
   int64_t n_qtiles, n_items, split_rows;
   uint64_t* lists;
   uint64_t* out;  // (splits, B, k)
+  const uint64_t* upper = nullptr;  // optional (B,): only keys strictly below upper[row] are admitted
 };
 
 cudaError_t launch_exact(const ExactParams& p, int grid, int cap, cudaStream_t stream);
@@ -68,6 +69,12 @@ struct RescoreParams {
   uint64_t* out;               // (B, k_out)
   int32_t* uncertified;        // (B,)
   int32_t* n_uncertified;      // device counter (caller zeroes)
+  // sharded re-scoring: the sorted exact keys of query row b are stored into the exchange buffer
+  // of the GPU that owns b, at [my_rank][b - owner*rows_per_owner][:k_out] (peer memory); no
+  // certificate is evaluated (out / uncertified / n_uncertified unused)
+  uint64_t* peer_out[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_peers = 0, my_rank = 0;
+  int64_t rows_per_owner = 0;
 };
 // workspace (optional, rescore_workspace_bytes): selects the TMA-pipelined two-kernel variant
 cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t workspace_bytes,
@@ -78,6 +85,14 @@ cudaError_t launch_certify(const RescoreParams& p, cudaStream_t stream);
 // split (n, k) key lists by owning shard: out (G, n, k), each shard's keys compacted to the front
 cudaError_t launch_route_keys(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int G,
                               uint64_t* out, cudaStream_t stream);
+// sharded_ops.cu
+cudaError_t launch_route_scatter(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int G,
+                                 uint64_t* const* inbox, int64_t row_offset, cudaStream_t stream);
+cudaError_t launch_compact_rows(const int64_t* status, int64_t ld, int64_t n, int64_t mask, int64_t* rows_out,
+                                int cap, int32_t* count_out, cudaStream_t stream);
+cudaError_t launch_scatter_rows(int64_t* dst, int64_t dst_ld, const int64_t* src, int64_t src_ld,
+                                const int64_t* rows, int n, const int32_t* count, int width,
+                                cudaStream_t stream);
 cudaError_t launch_row_norm_max(const float* a, const float* b, int64_t n, int dim_pad, float* out,
                                 cudaStream_t stream);
 
@@ -108,6 +123,6 @@ struct TcParams {
 cudaError_t launch_tc(const TcParams& p, int grid, int cap, cudaStream_t stream, float* dump,
                       int32_t* diag, int flags, const char** why);
 int tc_tile_n(int mode, int dim);
-bool tc_use_pair(int mode);  // BF16 runs as CTA pairs: a worker = 2 CTAs, query tile = 256 rows
+bool tc_use_pair(int mode, int64_t B);  // resident-query modes run as CTA pairs (256-row query tiles) when B > 128
 
 }  // namespace b200knn

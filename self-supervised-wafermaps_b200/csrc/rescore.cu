@@ -208,6 +208,9 @@ __global__ void __launch_bounds__(256)
   uint64_t p_key = load_key(pb, pg);
   uint64_t p_key_next = (pu + 1 < u_end) ? (pg + 1 < n_groups ? load_key(pb, pg + 1) : load_key(pb + 1, 0)) : 0ull;
 
+  // One pipeline step = (unit, chunk).  A unit without candidates (routed lists of the sharded
+  // mode use ~1/G of their slots) takes ONE step — no copies, just the barrier handshake — and
+  // the consumer, which sees the same all-empty key words, advances in the same way.
   auto produce = [&]() {
     Stage& st = stages[ps];
     const uint32_t bar = ptx::smem_u32(&bars[ps]);
@@ -221,8 +224,6 @@ __global__ void __launch_bounds__(256)
                uint32_t(len) * 4u, bar);
     const float* qrow = q32 + pb * p.q_ld;
     if (valid == 0u) {
-      // an empty unit (routed lists of the sharded mode use ~1/G of their slots): no copies at all,
-      // the stage only goes through its barrier handshake and the consumer skips the fma chain
     } else if (q_vec16) {
       for (int i = lane; i < len / 4; i += 32) {
         const int d = d0 + 4 * i;
@@ -236,9 +237,9 @@ __global__ void __launch_bounds__(256)
       }
     }
     cp_async_arrive_noinc(bar);
-    if (pc == 0) st.klo[lane] = uint32_t(p_key);
+    if (pc == 0) st.klo[lane] = row >= 0 ? uint32_t(p_key) : 0u;
     if (++ps == STAGES) ps = 0;
-    if (++pc == n_chunks) {
+    if (valid == 0u || ++pc == n_chunks) {
       pc = 0;
       ++pu;
       if (++pg == n_groups) {
@@ -257,15 +258,14 @@ __global__ void __launch_bounds__(256)
     }
   };
 
-  const int64_t n_steps = (u_end - u_begin) * n_chunks;
-  for (int64_t t = 0; t < STAGES && t < n_steps; ++t) produce();
+  for (int t = 0; t < STAGES && pu < u_end; ++t) produce();
 
   int cs = 0, cc = 0;
   uint32_t phase = 0, klo = 0;
   int64_t cu = u_begin;
   float acc = 0.0f;
   bool live = true;  // the unit holds at least one candidate
-  for (int64_t t = 0; t < n_steps; ++t) {
+  while (cu < u_end) {
     Stage& st = stages[cs];
     ptx::mbar_wait(ptx::smem_u32(&bars[cs]), phase, nullptr, 7);
     if (cc == 0) {
@@ -273,40 +273,42 @@ __global__ void __launch_bounds__(256)
       klo = st.klo[lane];
       live = __any_sync(kFull, klo != 0u);
     }
-    const int len4 = min(CHUNK, p.dim_pad - cc * CHUNK) / 4;
-    const float4* xr = reinterpret_cast<const float4*>(st.rows + lane * Stage::kPitch);
-    const float4* qr = reinterpret_cast<const float4*>(st.q);
-    // len4 is a multiple of 16 (dim_pad is a multiple of 64).  The 16 loads of a block are issued
-    // before its fma chain starts, and the next block's loads while the chain runs.
-    float4 x[8], w[8];
+    if (live) {
+      const int len4 = min(CHUNK, p.dim_pad - cc * CHUNK) / 4;
+      const float4* xr = reinterpret_cast<const float4*>(st.rows + lane * Stage::kPitch);
+      const float4* qr = reinterpret_cast<const float4*>(st.q);
+      // len4 is a multiple of 16 (dim_pad is a multiple of 64).  The 16 loads of a block are issued
+      // before its fma chain starts, and the next block's loads while the chain runs.
+      float4 x[8], w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      x[i] = xr[i];
-      w[i] = qr[i];
-    }
+      for (int i = 0; i < 8; ++i) {
+        x[i] = xr[i];
+        w[i] = qr[i];
+      }
 #pragma unroll 1
-    for (int j = 0; live && j < len4; j += 8) {
-      float4 xn[8], wn[8];
-      const int jn = (j + 8 < len4) ? j + 8 : j;
+      for (int j = 0; j < len4; j += 8) {
+        float4 xn[8], wn[8];
+        const int jn = (j + 8 < len4) ? j + 8 : j;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        xn[i] = xr[jn + i];
-        wn[i] = qr[jn + i];
-      }
+        for (int i = 0; i < 8; ++i) {
+          xn[i] = xr[jn + i];
+          wn[i] = qr[jn + i];
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc = __fmaf_rn(w[i].x, x[i].x, acc);
-        acc = __fmaf_rn(w[i].y, x[i].y, acc);
-        acc = __fmaf_rn(w[i].z, x[i].z, acc);
-        acc = __fmaf_rn(w[i].w, x[i].w, acc);
-      }
+        for (int i = 0; i < 8; ++i) {
+          acc = __fmaf_rn(w[i].x, x[i].x, acc);
+          acc = __fmaf_rn(w[i].y, x[i].y, acc);
+          acc = __fmaf_rn(w[i].z, x[i].z, acc);
+          acc = __fmaf_rn(w[i].w, x[i].w, acc);
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x[i] = xn[i];
-        w[i] = wn[i];
+        for (int i = 0; i < 8; ++i) {
+          x[i] = xn[i];
+          w[i] = wn[i];
+        }
       }
     }
-    if (++cc == n_chunks) {
+    if (!live || ++cc == n_chunks) {
       cc = 0;
       tmp[cu * 32 + lane] = klo != 0 ? ((uint64_t(f32_to_orderable(acc)) << 32) | uint64_t(klo)) : 0ull;
       ++cu;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(256)
     // the stage is free: order this warp's generic-proxy reads before the async-proxy refill
     __syncwarp();
     ptx::fence_proxy_async();
-    if (t + STAGES < n_steps) produce();
+    if (pu < u_end) produce();
     if (++cs == STAGES) {
       cs = 0;
       phase ^= 1;
@@ -322,7 +324,30 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// exact keys of one query (n_groups*32 slots in the workspace) -> best k_out, sorted; certificate
+// Sort the first `groups` 32-key groups of v descending with the smallest network that covers
+// them (the other groups are empty and stay where they are: zeros sort last anyway).
+template <int ITEMS>
+__device__ __forceinline__ void sort_groups(uint64_t (&v)[ITEMS], int groups, int lane) {
+  if (ITEMS > 2 && groups <= 2) {
+    uint64_t w[2] = {v[0], v[1]};
+    warp_sort_desc<2>(w, lane);
+    v[0] = w[0];
+    v[1] = w[1];
+  } else if (ITEMS > 4 && groups <= 4) {
+    uint64_t w[4] = {v[0], v[1], v[2], v[3]};
+    warp_sort_desc<4>(w, lane);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = w[r];
+  } else {
+    warp_sort_desc<ITEMS>(v, lane);
+  }
+}
+
+// exact keys of one query (n_groups*32 slots in the workspace) -> best k_out, sorted; certificate.
+// Sharded re-scoring (p.n_peers > 0): the sorted exact keys of query b go straight into the
+// exchange buffer of the GPU that owns query b (peer memory over NVLink), non-empty prefix only
+// (the owner zeroes its buffer before the exchange); no certificate here — the owner evaluates
+// it on the merged lists.
 template <int ITEMS>
 __global__ void __launch_bounds__(128)
     rescore_select_kernel(RescoreParams p, const uint64_t* __restrict__ tmp, int n_groups) {
@@ -331,14 +356,29 @@ __global__ void __launch_bounds__(128)
   if (b >= p.B) return;
   const uint64_t* mine = tmp + b * n_groups * 32;
   uint64_t v[ITEMS];
+  int groups = 0;  // groups holding at least one key (candidate lists are filled from the front)
 #pragma unroll
-  for (int r = 0; r < ITEMS; ++r) v[r] = r < n_groups ? mine[r * 32 + lane] : 0ull;
+  for (int r = 0; r < ITEMS; ++r) {
+    v[r] = r < n_groups ? mine[r * 32 + lane] : 0ull;
+    if (__any_sync(kFull, v[r] != 0ull)) groups = r + 1;
+  }
+  sort_groups<ITEMS>(v, groups, lane);
+  if (p.n_peers > 0) {
+    const int64_t owner = b / p.rows_per_owner;
+    uint64_t* o = p.peer_out[owner] +
+                  (int64_t(p.my_rank) * p.rows_per_owner + (b - owner * p.rows_per_owner)) * p.k_out;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = r * 32 + lane;
+      if (i < p.k_out && v[r] != 0ull) o[i] = v[r];
+    }
+    return;
+  }
   const float* qrow = static_cast<const float*>(p.q) + b * p.q_ld;
   float qq = 0.0f;
   for (int d = lane; d < p.dim; d += 32) qq = fmaf(qrow[d], qrow[d], qq);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(kFull, qq, o);
-  warp_sort_desc<ITEMS>(v, lane);
   uint64_t kth = 0;
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
@@ -484,6 +524,7 @@ cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t works
   const bool pipelined = workspace != nullptr && workspace_bytes >= rescore_workspace_bytes(p.B, p.k_in) &&
                          p.rows_b == nullptr && p.q_dtype == B200KNN_F32 &&
                          reinterpret_cast<uintptr_t>(p.rows_a) % 16 == 0;
+  if (p.n_peers > 0 && !pipelined) return cudaErrorInvalidValue;  // the scatter lives in the pipelined variant
   if (pipelined) {
     uint64_t* tmp = static_cast<uint64_t*>(workspace);
     cudaError_t e = dot_chunk() == 256 ? launch_dot_t<256, 2>(p, tmp, items, stream)

@@ -1,0 +1,9 @@
+// tc_inst_bf16_single.cu — tc_topk_kernel<B200KNN_MODE_BF16, *, *, *, PAIR=false> (see tc_topk_impl.cuh).
+#include "tc_inst.h"
+#include "tc_topk_impl.cuh"
+
+namespace b200knn {
+B200KNN_TC_LAUNCHER(launch_tc_bf16_single) {
+  return launch_variant<B200KNN_MODE_BF16, false>(p, grid, cap, stream, dump, diag, flags, why);
+}
+}  // namespace b200knn

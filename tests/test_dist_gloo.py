@@ -87,10 +87,10 @@ class OracleOps:
     # ---- sharded fp32 mode (same contract as _CudaOps)
     @staticmethod
     def cascade_levels(bank_shard, mode):
-        from b200knn.knn import LEVELS
+        from b200knn.knn import level_config
         if mode != "fp32":
             return None
-        return [dict(LEVELS[name], name=name) for name in ("fp32_f16", "fp32_f16x2")]
+        return [level_config(name, bank_shard.shape[0]) for name in ("fp32_f16", "fp32_f16x2")]
 
     @staticmethod
     def route_keys(keys, rows_per_shard, n_shards):
@@ -132,6 +132,33 @@ class OracleOps:
     def bank_max_norm(bank_shard, cand_mode):
         return torch.tensor([float(np.linalg.norm(bank_shard.numpy(), axis=0).max()) * 1.001])
 
+    # ---- device-side hand-over to the second level (same contract as _CudaOps)
+    l2_fail_rank = -1  # >= 0: that rank's shard-local certificate fails for the first open row
+
+    @staticmethod
+    def compact_rows(packed, col, mask, cap):
+        idx = torch.nonzero((packed[:, col] & mask) != 0).view(-1)
+        rows = torch.zeros((cap,), dtype=torch.int64)
+        rows[:min(cap, idx.numel())] = idx[:cap]
+        return rows, torch.tensor([idx.numel()], dtype=torch.int32)
+
+    @staticmethod
+    def scatter_rows(dst, src, rows, count):
+        m = min(rows.numel(), int(count))
+        dst[rows[:m]] = src[:m]
+
+    @classmethod
+    def local_exact_keys(cls, feature, bank_shard, k, mode, idx_offset):
+        B, n = feature.shape[0], bank_shard.shape[1]
+        out = torch.zeros((B, k + 1), dtype=torch.int64)
+        k_loc = min(k, n)
+        if B and k_loc:
+            s, i = O.canonical_topk_c(O.sims_seqfma(feature.numpy(), bank_shard.numpy()), k_loc, idx_offset)
+            out[:, :k_loc] = torch.from_numpy(O.make_keys(s, i).view(np.int64))
+            if cls.l2_fail_rank == dist.get_rank():
+                out[0, k] = 1
+        return out
+
 
 def _free_port():
     with socket.socket() as s:
@@ -139,7 +166,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, out_dir, stride=0, poison=False, mode="bf16", force_uncertified=False):
+def _worker(rank, world, port, case, out_dir, stride=0, poison=False, mode="bf16", force_uncertified=False,
+            l2_fail_rank=-1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -147,6 +175,7 @@ def _worker(rank, world, port, case, out_dir, stride=0, poison=False, mode="bf16
 
         OracleOps.sample_stride, OracleOps.poison_threshold = stride, poison
         OracleOps.force_uncertified = force_uncertified
+        OracleOps.l2_fail_rank = l2_fail_rank
         c = datagen.make_case(case)
         bank = torch.from_numpy(c["bank"])
         sb = ShardedBank.from_full(bank, torch.from_numpy(c["labels"]), ops=OracleOps, mode=mode)
@@ -204,6 +233,22 @@ def test_sharded_fp32_rescored_at_row_owner(world, case, stride, poison, force, 
         # (the emulated pre-pass, 16 best of every 4th row, is tighter than the product's stride rule
         # and starves some rows of their k + margin candidates: those legitimately take the fallback)
         assert (redo >= world) if force else (redo >= 1 if poison else (redo == 0 or stride > 0))
+
+
+@pytest.mark.parametrize("world,fail_rank", [(2, 0), (3, 2)])
+def test_sharded_fp32_one_shard_fails_its_local_certificate(world, fail_rank, tmp_path):
+    """The first level leaves one row per rank open; at the second level ONE rank's shard-local
+    certificate fails while the others pass.  Every decision is derived from all-gathered data (no
+    per-process cascade state), so the ranks stay in lock-step — no mismatched collective — and the
+    row takes the host-driven path on every rank; results stay bit for bit the oracle's."""
+    mp.spawn(_worker, args=(world, _free_port(), "mixed38", str(tmp_path), 4, False, "fp32", True, fail_rank),
+             nprocs=world, join=True)
+    c = datagen.make_case("mixed38")
+    s, i = O.topk_seqfma(c["feature"], c["bank"], c["k"])
+    want_pred = O.vote_o64(s, i, c["labels"], c["C"], c["t"])[0]
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"pred_{r}.npy"), want_pred)
+        assert np.array_equal(np.load(tmp_path / f"keys_{r}.npy"), O.make_keys(s, i).view(np.int64))
 
 
 def test_shard_smaller_than_k(tmp_path):

@@ -78,7 +78,7 @@ def test_tiles_and_selection(name, _, mode):
         ref = qh @ bh.T
         qn, bn = np.linalg.norm(q, axis=1).max(), np.linalg.norm(bank, axis=0).max()
         tol = 2e-6 * max(1.0, qn * bn)
-        lv = K.LEVELS["fp32_f16"]  # and against the true similarities: the certificate bound
+        lv = K.level_config("fp32_f16", D)  # and against the true similarities: the certificate bound
         bound = lv["err_coef"] * qn * bn + lv["err_abs"] * np.sqrt(K.padded_dim(D)) * (qn + bn)
         assert np.abs(dump.astype(np.float64) - q.astype(np.float64) @ bank.astype(np.float64)).max() <= bound
     elif mode == "f16x2":
@@ -92,7 +92,7 @@ def test_tiles_and_selection(name, _, mode):
         qn, bn = np.linalg.norm(q, axis=1).max(), np.linalg.norm(bank, axis=0).max()
         tol = 4e-6 * max(1.0, qn * bn)
         # and against the true similarities: the certificate bound of level fp32_f16x2
-        lv = K.LEVELS["fp32_f16x2"]
+        lv = K.level_config("fp32_f16x2", D)
         bound = lv["err_coef"] * qn * bn + lv["err_abs"] * np.sqrt(K.padded_dim(D)) * (qn + bn)
         assert np.abs(dump.astype(np.float64) - q.astype(np.float64) @ bank.astype(np.float64)).max() <= bound
     elif mode == "bf16x3":
@@ -363,8 +363,6 @@ def test_k_limits_and_empty_batch():
     bank = torch.randn(N, D, device=DEV).t().contiguous()
     q = torch.randn(4, D, device=DEV)
     for mode in ("exact", "bf16", "fp32"):
-        with pytest.raises(RuntimeError):
-            b200knn.topk_keys(q, bank, 993, mode=mode)          # list capacity: k <= 992
         with pytest.raises(RuntimeError, match="out of range"):
             b200knn.topk_keys(q, bank, N + 1, mode=mode)
         empty = b200knn.topk_keys(q[:0], bank, 10, mode=mode)

@@ -125,10 +125,11 @@ def test_fp16_candidate_levels_operand_error_bounds():
         f16  : |q16.x16 - q.x|          <= 2^-10 (1+2^-12) |q||x| + 2^-25 sqrt(D) (|q|+|x|)
         f16x2: |q16.(x_hi+x_lo) - q.x|  <= (2^-11 + 2^-22)(1+2^-11) |q||x| + 2^-25 sqrt(D) (|q|+|x|)
     including fp16's subnormal range (the 2^-25 terms).  The levels' err_coef / err_abs must dominate
-    these (the remainder of err_coef is the stated allowance for the fp32 accumulation in TMEM)."""
+    these (the remainder of err_coef is the D-scaled worst-case allowance for the accumulation in the
+    tensor core, acc_c * D_pad * 2^-23, see b200knn/knn.py)."""
     import numpy as np
 
-    from b200knn.knn import LEVELS
+    from b200knn.knn import level_config
 
     rng = np.random.default_rng(0)
     D = 512
@@ -153,8 +154,8 @@ def test_fp16_candidate_levels_operand_error_bounds():
             bound = coef * qn * xn + tail
             assert (err <= bound).all(), (name, scale_q, scale_x, float((err / bound).max()))
             worst[name] = max(worst[name], float((err / bound).max()))
-            lv = LEVELS["fp32_" + name]
-            assert lv["err_coef"] >= coef and lv["err_abs"] >= 2.0 ** -25 and lv["max_abs"] < 65504.0
+            lv = level_config("fp32_" + name, D)
+            assert lv["op_coef"] >= coef and lv["err_coef"] >= lv["op_coef"] + lv["acc_c"] * D * 2.0 ** -23 and lv["err_coef"] >= coef and lv["err_abs"] >= 2.0 ** -25 and lv["max_abs"] < 65504.0
             # the certificate's E (host side multiplies err_abs by sqrt(padded D)) dominates the bound
             e_cert = lv["err_coef"] * qn * xn + lv["err_abs"] * np.sqrt(D) * (qn + xn)
             assert (e_cert >= bound).all()
