@@ -108,26 +108,58 @@ LEVELS = {
 }
 
 
-def level_config(name: str, dim: int) -> dict:
-    """LEVELS[name] with the certificate's err_coef resolved for vectors of dimension `dim`."""
-    cfg = dict(LEVELS[name], name=name)
+def level_config(spec: str, dim: int) -> dict:
+    """The level `spec` = "<LEVELS name>" or "<LEVELS name>@<margin>" (a wider candidate margin than
+    the level's default) with the certificate's err_coef resolved for vectors of dimension `dim`."""
+    name, _, margin = spec.partition("@")
+    cfg = dict(LEVELS[name], name=spec)
+    if margin:
+        cfg["margin"] = int(margin)
     cfg["err_coef"] = cfg["op_coef"] + 1.01 * cfg["acc_c"] * padded_dim(dim) * ACC_ULP
     return cfg
 
 
-# mode -> levels tried in order (then "exact").  "fp32" skips its BF16 level for a bank on which
-# that level recently left more than CASCADE_GIVE_UP of the rows uncertified.
-CASCADES = {"fp32": ("fp32_f16", "fp32_f16x2", "fp32_bf16x3", "fp32_tf32"), "fp32_f16": ("fp32_f16",),
+# mode -> levels tried in order (then "exact").  What decides whether a row certifies is the
+# candidate margin against the level's error bound E: the exact k-th similarity must beat the
+# approximate (k + margin)-th by E, i.e. the row's similarities must spread by E over `margin`
+# ranks.  Embeddings whose similarities are bunched (dense non-negative rows: every pair of rows is
+# similar) need a wider margin, not more MMAs — re-scoring 80 more candidates costs a few percent,
+# a second MMA per k-step doubles the pass.  So "fp32" runs
+#   fp16 (1 MMA, margin 40 x boost)  ->  fp16 x split-fp16 (2 MMAs) with margin 160
+#   ->  the same with the widest margin the lists allow (k_in = 992)  ->  exact kernel,
+# where boost in {1, 2, 4} follows the fraction of rows the first level left uncertified on this
+# bank (CASCADE_WIDEN / CASCADE_NARROW), and the first level is skipped for CASCADE_RETRY_CALLS
+# calls if even the widest boost leaves more than CASCADE_GIVE_UP.  Vectors wider than the resident
+# query tile (D_pad > 768) use the split-BF16 kernel at every level.  These statistics are
+# per-process state of the single-GPU path; the sharded driver keeps its own, derived from
+# all-gathered counts only, so that every rank takes the same decisions.
+CASCADES = {"fp32": ("fp32_f16", "fp32_f16x2@160", "fp32_f16x2@992"), "fp32_f16": ("fp32_f16",),
             "fp32_f16x2": ("fp32_f16x2",),
             "fp32_bf16x3": ("fp32_bf16x3",),
             "fp32_bf16": ("fp32_bf16",), "fp32_tf32": ("fp32_tf32",)}
+CASCADE_WIDE = ("fp32_bf16x3@64", "fp32_bf16x3@992")  # "fp32" when D_pad > MAX_BF16_DIM
 CASCADE_GIVE_UP = 0.25
 CASCADE_RETRY_CALLS = 64
-# The cascade's first level is skipped for CASCADE_RETRY_CALLS calls on a bank where it left more
-# than CASCADE_GIVE_UP of the rows uncertified (single-GPU path only: the sharded driver derives
-# every decision from all-gathered data, never from per-process state).
+CASCADE_WIDEN = 0.03     # more than this fraction uncertified: double the first level's margin (up to x4)
+CASCADE_NARROW = 0.003   # less than this for CASCADE_CALM_CALLS calls in a row: halve it again
+CASCADE_CALM_CALLS = 16
+CASCADE_MAX_BOOST = 4
+
+
+def next_boost(boost: int, calm: int, rows: int, uncertified: int):
+    """(boost, calm) after a call that left `uncertified` of `rows` rows uncertified at the first level."""
+    if rows < 128:
+        return boost, calm
+    frac = uncertified / rows
+    if frac > CASCADE_WIDEN and boost < CASCADE_MAX_BOOST:
+        return boost * 2, 0
+    if frac < CASCADE_NARROW and boost > 1:
+        return (boost // 2, 0) if calm + 1 >= CASCADE_CALM_CALLS else (boost, calm + 1)
+    return boost, 0
+
+
 # first level of each mode (bench / docs)
-RESCORED_MODES = {m: LEVELS[c[0]] for m, c in CASCADES.items()}
+RESCORED_MODES = {m: LEVELS[c[0].partition("@")[0]] for m, c in CASCADES.items()}
 ALL_MODES = tuple(_lib.MODES) + tuple(RESCORED_MODES)
 
 # statistics of the last rescored call (bench / tests): rows that failed the certificate
@@ -744,9 +776,10 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
 
 # ---- pieces of the sharded fp32 mode (b200knn/sharded.py): candidates are merged by the owner of
 # a query, re-scored by the shard that owns each candidate's bank row, merged again and certified
-def cascade_levels(feature_bank: torch.Tensor, mode: str) -> list:
+def cascade_levels(feature_bank: torch.Tensor, mode: str, boost: int = 1) -> list:
     """The candidate levels a rescored mode tries in order on this bank (LEVELS entries + names)."""
-    return [level_config(name, feature_bank.shape[0]) for name in _cascade_levels(feature_bank, mode, track=False)]
+    return [level_config(name, feature_bank.shape[0])
+            for name in _cascade_levels(feature_bank, mode, track=False, boost=boost)]
 
 
 def route_keys(keys: torch.Tensor, rows_per_shard: int, n_shards: int) -> torch.Tensor:
@@ -909,19 +942,27 @@ def bank_max_norm(feature_bank: torch.Tensor, cand_mode: str) -> torch.Tensor:
     return bank_cache.get(feature_bank, cand_mode).max_norm()
 
 
-def _cascade_levels(feature_bank: torch.Tensor, mode: str, track: bool = True):
-    """track=False (sharded driver): the fixed level list of the mode — the per-process "skip the
-    first level" statistics are neither read nor decremented, so every rank of a process group
-    derives the same list (ranks that disagreed would mismatch their collectives)."""
+def _cascade_levels(feature_bank: torch.Tensor, mode: str, track: bool = True, boost: int = 1):
+    """The level specs `mode` tries in order on this bank.  track=False (sharded driver, captured
+    graphs): the per-process statistics (margin boost, "skip the first level") are neither read nor
+    updated — the caller passes its own `boost` — so every rank of a process group derives the
+    same list (ranks that disagreed would mismatch their collectives)."""
     levels = list(CASCADES[mode])
     if len(levels) > 1 and padded_dim(feature_bank.shape[0]) > MAX_BF16_DIM:
-        # no resident query tile at this width: start at the split-BF16 level
-        levels = [lv for lv in levels if LEVELS[lv]["cand"] not in ("f16", "f16x2")]
-    if len(levels) > 1 and track:
-        st = bank_cache.state(feature_bank)
-        if st.get("skip_first", 0) > 0:
-            st["skip_first"] -= 1
+        levels = list(CASCADE_WIDE)  # no resident query tile at this width
+    if len(levels) > 1:
+        skip = False
+        if track:
+            st = bank_cache.state(feature_bank)
+            boost = st.get("boost", 1)
+            if st.get("skip_first", 0) > 0:
+                st["skip_first"] -= 1
+                skip = True
+        if skip:
             levels = levels[1:]
+        elif boost > 1:
+            name = levels[0].partition("@")[0]
+            levels[0] = f"{name}@{level_config(levels[0], 1)['margin'] * boost}"
     return levels
 
 
@@ -946,13 +987,18 @@ def _note_first_level(feature_bank: torch.Tensor, mode: str, levels, rows: int, 
     last_rescore_stats["rows"], last_rescore_stats["uncertified"] = rows, uncertified
     last_rescore_stats["level"] = levels[0]
     last_rescore_stats["levels"] = [(levels[0], rows, uncertified)]  # (level, rows in, rows left uncertified)
-    if track and len(CASCADES[mode]) > 1 and levels[0] == CASCADES[mode][0] and rows > 0 \
-            and uncertified > CASCADE_GIVE_UP * rows:
-        bank_cache.state(feature_bank)["skip_first"] = CASCADE_RETRY_CALLS
+    first = CASCADES[mode][0].partition("@")[0]
+    if track and len(CASCADES[mode]) > 1 and levels[0].partition("@")[0] in (first, CASCADE_WIDE[0].partition("@")[0]) \
+            and rows > 0:
+        st = bank_cache.state(feature_bank)
+        boost = st.get("boost", 1)
+        if boost >= CASCADE_MAX_BOOST and rows >= 128 and uncertified > CASCADE_GIVE_UP * rows:
+            st["skip_first"] = CASCADE_RETRY_CALLS
+        st["boost"], st["calm"] = next_boost(boost, st.get("calm", 0), rows, uncertified)
 
 
 def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
-                        idx_offset: int = 0, defer: bool = False, track: bool = True):
+                        idx_offset: int = 0, defer: bool = False, track: bool = True, boost: int = 1):
     """Tensor-core candidates -> exact sequential-fma re-scoring -> best k, with a per-row
     certificate; rows a level cannot certify go to the next level and finally to the "exact"
     kernel, so the keys are bitwise those of mode "exact".
@@ -968,7 +1014,7 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
     if B == 0:
         out = torch.empty((B, k), dtype=torch.int64, device=dev)
         return (out, None, None, None) if defer else out
-    levels = _cascade_levels(feature_bank, mode, track)
+    levels = _cascade_levels(feature_bank, mode, track, boost)
     out, flags, n_bad = _rescored_level(feature, feature_bank, k, levels[0], idx_offset)
 
     def fix(rows, n_rows_bad):
@@ -1050,14 +1096,14 @@ def vote(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn
 # ----------------------------------------------------------------------------
 # the reference's public symbols for this path
 # ----------------------------------------------------------------------------
-def _predict_enqueue(feature, feature_bank, feature_labels, num_classes, knn_k, knn_t, mode, track=True):
+def _predict_enqueue(feature, feature_bank, feature_labels, num_classes, knn_k, knn_t, mode, track=True, boost=1):
     """Everything of one tensor-core-mode call, enqueued without a host synchronisation (so it can
     be captured into a CUDA graph): (pred (B,C), status int32[2] = [vote flag, rows to recompute],
     bad_rows (B,) mask/flags, fix).  status[0]: 1 label / 2 neighbour index out of range;
     status[1]: rows a sampled threshold starved, or rows whose re-scoring could not be certified."""
     if mode in RESCORED_MODES:
         keys, bad_rows, n_bad, fix = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True,
-                                                         track=track)
+                                                         track=track, boost=boost)
     else:
         keys = topk_keys(feature, feature_bank, knn_k, mode, repair=False)
         bad_rows = keys[:, -1] == 0
@@ -1110,8 +1156,15 @@ class _CallGraph:
 _call_graphs = {}
 
 
+def _graph_boost(feature_bank, mode) -> int:
+    """The first level's margin boost a captured call of this bank uses (part of the graph key)."""
+    if mode in RESCORED_MODES and len(CASCADES[mode]) > 1:
+        return bank_cache.state(feature_bank).get("boost", 1)
+    return 1
+
+
 def _graph_key(feature, feature_bank, labels, num_classes, knn_k, knn_t, mode):
-    return (feature_bank.data_ptr(), feature_bank._version, tuple(feature_bank.shape), tuple(feature_bank.stride()),
+    return (_graph_boost(feature_bank, mode), feature_bank.data_ptr(), feature_bank._version, tuple(feature_bank.shape), tuple(feature_bank.stride()),
             feature_bank.dtype, feature_bank.device.index, labels.data_ptr(), labels._version,
             tuple(feature.shape), feature.dtype, int(num_classes), int(knn_k), float(knn_t), mode)
 
@@ -1132,14 +1185,15 @@ def _graph_for(feature, feature_bank, labels, num_classes, knn_k, knn_t, mode):
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):  # warm-up on a side stream, as graph capture requires
         query_cache.clear()
-        _predict_enqueue(entry.q_static, feature_bank, labels, num_classes, knn_k, knn_t, mode, track=False)
+        _predict_enqueue(entry.q_static, feature_bank, labels, num_classes, knn_k, knn_t, mode, track=False,
+                         boost=key[0])
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize(dev)
     query_cache.clear()
     entry.graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(entry.graph):
         pred, status, bad_rows, fix = _predict_enqueue(entry.q_static, feature_bank, labels, num_classes, knn_k,
-                                                       knn_t, mode, track=False)
+                                                       knn_t, mode, track=False, boost=key[0])
         entry.status_host.copy_(status, non_blocking=True)
     query_cache.clear()  # it now refers to tensors of the graph's private pool
     entry.pred, entry.bad_rows, entry.fix = pred, bad_rows, fix
@@ -1195,6 +1249,10 @@ def knn_predict(feature: torch.Tensor, feature_bank: torch.Tensor, feature_label
             pred = g.pred.clone()
             torch.cuda.current_stream().synchronize()
             graph_stats["replays"] += 1
+            if mode in RESCORED_MODES and len(CASCADES[mode]) > 1:
+                st = bank_cache.state(feature_bank)  # the margin boost follows the captured calls too
+                st["boost"], st["calm"] = next_boost(st.get("boost", 1), st.get("calm", 0), feature.shape[0],
+                                                     int(g.status_host[1]))
             if not g.status_host.any():
                 return pred
             # rows to recompute / label errors: the ordinary host side, on the graph's own buffers

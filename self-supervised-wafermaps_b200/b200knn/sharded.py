@@ -104,9 +104,9 @@ class _CudaOps:
 
     # ---- sharded fp32 mode: candidate level, routing, re-scoring of routed candidates, certificate
     @staticmethod
-    def cascade_levels(bank_shard, mode):
+    def cascade_levels(bank_shard, mode, boost=1):
         from .knn import RESCORED_MODES, cascade_levels
-        return cascade_levels(bank_shard, mode) if mode in RESCORED_MODES else None
+        return cascade_levels(bank_shard, mode, boost) if mode in RESCORED_MODES else None
 
     @staticmethod
     def route_keys(keys, rows_per_shard, n_shards):
@@ -469,9 +469,12 @@ class ShardedBank:
         self._mark("vote+gather")
         return gathered
 
-    # capacity of the device-side second level, per batch size (doubles after an overflow; every
-    # rank sees the same counts, so every rank keeps the same value)
+    # capacity of the device-side second level, per batch size (doubles after an overflow), and the
+    # first level's margin boost (knn.next_boost).  Both follow the all-gathered count of open rows
+    # only, so every rank keeps the same values and takes the same decisions.
     _l2_cap = None
+    _boost = 1
+    _calm = 0
 
     def _knn_predict_rescored(self, feature, C, knn_k, knn_t, levels) -> torch.Tensor:
         """Sharded fp32 mode, ONE host synchronisation per call.
@@ -514,6 +517,9 @@ class ShardedBank:
         self.last_uncertified = int(host[4]) if n_open is not None else int(((status & 9) != 0).sum().item())
         if n_open is not None and host[4] > cap:
             self._l2_cap[B] = min(B, 2 * max(cap, int(host[4])))
+        if len(levels) > 1:
+            from .knn import next_boost
+            self._boost, self._calm = next_boost(self._boost, self._calm, B, self.last_uncertified)
         if host[0] or host[3]:
             # host-driven path (identical status on every rank -> matched collectives): per-shard
             # exact top-k through the single-GPU cascade, all-gathered and merged
@@ -541,7 +547,8 @@ class ShardedBank:
             raise ValueError(f"unknown exchange {exchange!r}")
         if knn_k > self.n_rows:
             raise RuntimeError("selected index k out of range")
-        levels = self.ops.cascade_levels(self.bank_shard, self.mode) if hasattr(self.ops, "cascade_levels") else None
+        levels = self.ops.cascade_levels(self.bank_shard, self.mode, self._boost) \
+            if hasattr(self.ops, "cascade_levels") else None
         if levels and self.rescore_at_row_owner and feature.shape[0] > 0:
             return self._knn_predict_rescored(feature, int(num_classes), knn_k, knn_t, levels)
         B, C = feature.shape[0], int(num_classes)

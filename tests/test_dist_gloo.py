@@ -86,7 +86,7 @@ class OracleOps:
 
     # ---- sharded fp32 mode (same contract as _CudaOps)
     @staticmethod
-    def cascade_levels(bank_shard, mode):
+    def cascade_levels(bank_shard, mode, boost=1):
         from b200knn.knn import level_config
         if mode != "fp32":
             return None
