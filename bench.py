@@ -630,8 +630,8 @@ def main():
         # kernels launched through the C ABI inside the timed region (counted by the loader
         # proxy) + the split merges b200knn_topk* adds internally when its plan splits the bank
         splits_extra = args.steps if plan["splits"] > 1 else 0
-        if K.prepass_stride(N, k_plan) and mode != "exact":
-            sp = b200knn.plan_info(Q, max(1, n_local // K.prepass_stride(N, k_plan)), DIM, K.PREPASS["r"], cand_mode)
+        if K.prepass_stride(N, k_plan, Q) and mode != "exact":
+            sp = b200knn.plan_info(Q, max(1, n_local // K.prepass_stride(N, k_plan, Q)), DIM, K.PREPASS["r"], cand_mode)
             splits_extra += args.steps if sp["splits"] > 1 else 0
         gpu_launches = n_abi_kernels + splits_extra
         elem = {"bf16": 2, "f16": 2, "bf16x3": 4, "f16x2": 2, "tf32x3": 8, "exact": 4}[cand_mode]
@@ -677,7 +677,7 @@ def main():
         if rescored:
             line["config"]["uncertified_rows_last_step"] = uncertified
             line["config"]["cascade_last_step"] = rescore_stats.get("levels") if world == 1 else None
-        line["config"]["prepass"] = {"stride": K.prepass_stride(N, k_plan), "r": K.PREPASS["r"],
+        line["config"]["prepass"] = {"stride": K.prepass_stride(N, k_plan, Q), "r": K.PREPASS["r"],
                                      "repaired_rows_last_step": prepass_stats["repaired"]}
         line.update(side)
         del side

@@ -477,14 +477,20 @@ def _check_feature_bank(feature: torch.Tensor, feature_bank: torch.Tensor) -> No
 # otherwise pays as a fixed cost; rows where the bound fails end with an empty k-th slot and are
 # recomputed without it.
 PREPASS = {"enabled": os.environ.get("B200KNN_PREPASS", "1") == "1", "r": 16, "rank_factor": 5.0,
-           "min_k": 64, "min_sample_rows": 1024,
+           "min_k": 64, "min_sample_rows": 1024, "small_batch": 512,
            # r == 16: use the values-only kernel variant (row top-16 in registers) for the sample
            "register_sample": os.environ.get("B200KNN_REGISTER_SAMPLE", "1") == "1"}
 
 
-def prepass_stride(n_rows: int, k: int) -> int:
-    """Row stride of the sampling pre-pass, or 0 when it does not pay (small k or small bank)."""
-    if not PREPASS["enabled"] or k < PREPASS["min_k"]:
+def prepass_stride(n_rows: int, k: int, batch: Optional[int] = None) -> int:
+    """Row stride of the sampling pre-pass, or 0 when it does not pay.  Large batches: only for
+    k >= min_k (short lists warm up quickly).  Small batches (the reference-shaped B = 64 call) are
+    planned with one bank split per SM, every split pays the list warm-up and its merge handles
+    `splits` lists per row: there the threshold pays for any k (measured at N = 37,348, k = 5+40:
+    125 us of warm-up prunes + 60 us of merge without it)."""
+    if not PREPASS["enabled"]:
+        return 0
+    if k < PREPASS["min_k"] and (batch is None or batch > PREPASS["small_batch"]):
         return 0
     s = max(8, min(256, int(round(PREPASS["rank_factor"] * k / PREPASS["r"]))))
     return s if n_rows // s >= PREPASS["min_sample_rows"] else 0
@@ -550,10 +556,10 @@ def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode:
                 n_rows_for_decision: Optional[int] = None) -> Optional[torch.Tensor]:
     """Pre-pass: (B, r) best keys among every s-th bank row, or None when the pre-pass is off."""
     N = feature_bank.shape[1]
-    s = prepass_stride(n_rows_for_decision if n_rows_for_decision is not None else N, k)
+    B, D = feature.shape
+    s = prepass_stride(n_rows_for_decision if n_rows_for_decision is not None else N, k, B)
     if s == 0 or mode not in TC_MODES:
         return None
-    B, D = feature.shape
     mode = effective_mode(mode, D)
     r = PREPASS["r"]
     n_visit = (N + s - 1) // s
