@@ -209,6 +209,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def elem_bytes(cand_mode):
+    return {"bf16": 2, "f16": 2, "bf16x3": 4, "f16x2": 2, "tf32x3": 8, "exact": 4}[cand_mode]
+
+
 def metric_name():
     return METRIC if (N_BANK, DIM, KNN_K) == (811457, 512, 200) else f"kNN queries/s @{N_BANK}x{DIM} bank, k={KNN_K}"
 
@@ -591,7 +595,10 @@ def main():
         ms_per_step = total_ms / args.steps
         value = Q / (ms_per_step * 1e-3)
         flops = 2.0 * Q * n_local * DIM  # algorithmic: 2*N*D per query, this rank's rows
-        achieved = flops / (max(topk_ms, 1e-9) * 1e-3) / 1e12
+        whole_call = topk_ms <= 0.0  # captured (CUDA-graph) calls: no per-kernel events, time the whole call
+        if whole_call:
+            topk_ms = ms_per_step
+        achieved = flops / (topk_ms * 1e-3) / 1e12
         cand_mode = K.RESCORED_MODES[mode]["cand"] if rescored else mode
         margin = K.RESCORED_MODES[mode]["margin"] if rescored else 0
         k_plan = KNN_K + margin
@@ -620,6 +627,12 @@ def main():
                     "step_frac": flops / (ms_per_step * 1e-3) / 1e12 / peak}
             if mmas > 1:
                 roof["executed_frac"] = mmas * achieved / peak
+            if whole_call:
+                hbm_floor_ms = n_local * K.padded_dim(DIM) * elem_bytes(cand_mode) / (pk["hbm"] * 1e9) * 1e3
+                roof["kernel"] = ("whole captured call (CUDA graph of ~12 kernels, B <= 512): launch-latency bound, "
+                                  "not tensor bound; kernel_ms is the call")
+                roof["latency_bound"] = {"us_per_call": ms_per_step * 1e3, "hbm_floor_us": hbm_floor_ms * 1e3,
+                                         "note": "floor = candidate bank streamed once; a bank that fits L2 has no HBM floor"}
         if rescored and rescore_ms > 0:
             k_in = min(N, k_plan)
             gb = Q * k_in * K.padded_dim(DIM) * 4.0 / world / 1e9  # candidate rows gathered by this rank
@@ -634,7 +647,7 @@ def main():
             sp = b200knn.plan_info(Q, max(1, n_local // K.prepass_stride(N, k_plan, Q)), DIM, K.PREPASS["r"], cand_mode)
             splits_extra += args.steps if sp["splits"] > 1 else 0
         gpu_launches = n_abi_kernels + splits_extra
-        elem = {"bf16": 2, "f16": 2, "bf16x3": 4, "f16x2": 2, "tf32x3": 8, "exact": 4}[cand_mode]
+        elem = elem_bytes(cand_mode)
         bank_mb = n_local * K.padded_dim(DIM) * elem / 1e6
         step_mb = (Q * DIM * 4 + Q * k_plan * 8 + (Q * min(N, k_plan) * K.padded_dim(DIM) * 4 / world if rescored else 0)) / 1e6
         l2_note = (f"candidate bank {bank_mb:.0f} MB per rank "

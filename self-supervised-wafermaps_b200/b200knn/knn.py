@@ -744,8 +744,10 @@ def _repair_rows(keys: torch.Tensor, recompute) -> torch.Tensor:
 last_prepass_stats = {"rows": 0, "repaired": 0}
 
 
-def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, level: str, idx_offset: int):
-    """One cascade level, nothing synchronises: (keys (B,k), uncertified flags (B,) int32, count int32[1])."""
+def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, level: str, idx_offset: int,
+                    n_bad: Optional[torch.Tensor] = None):
+    """One cascade level, nothing synchronises: (keys (B,k), uncertified flags (B,) int32, count int32[1]).
+    n_bad: optional zeroed int32[1] the count is accumulated into (the caller's status word)."""
     lib = _lib.load()
     B, D = feature.shape
     cfg = level_config(level, D)
@@ -767,7 +769,8 @@ def _rescored_level(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, l
     out = torch.empty((B, k), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         flags = torch.empty((B,), dtype=torch.int32, device=dev)
-        n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        if n_bad is None:
+            n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
         ws_bytes = int(lib.b200knn_rescore_workspace_bytes(B, k_in)) if rows_b is None else 0
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
         with _Timed("rescore"):
@@ -903,12 +906,14 @@ def scatter_rows(dst: torch.Tensor, src: torch.Tensor, rows: torch.Tensor, count
 def local_exact_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
                      idx_offset: int) -> torch.Tensor:
     """(B, k+1) int64, nothing synchronises: columns [0, k) the exact top-min(k, N) keys of this bank
-    (zero-padded) from the SECOND level of `mode`'s cascade (the last one if it has only one),
-    column k = 1 where that level's certificate failed."""
+    (zero-padded) from the SECOND level of `mode`'s cascade at its base margin (the last level if
+    there is only one), column k = 1 where that level's certificate failed.  Base margin: a
+    shard holds 1/G of the bank, so its rank gaps are already G times wider than the global ones
+    the first level failed on, and the sub-batch stays cheap (shorter lists, fewer rows to gather)."""
     B = feature.shape[0]
     N = feature_bank.shape[1]
     levels = _cascade_levels(feature_bank, mode, track=False)
-    level = levels[1] if len(levels) > 1 else levels[0]
+    level = (levels[1] if len(levels) > 1 else levels[0]).partition("@")[0]
     k_loc = min(int(k), N)
     out = torch.zeros((B, k + 1), dtype=torch.int64, device=feature.device)
     if B and k_loc:
@@ -1004,7 +1009,8 @@ def _note_first_level(feature_bank: torch.Tensor, mode: str, levels, rows: int, 
 
 
 def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
-                        idx_offset: int = 0, defer: bool = False, track: bool = True, boost: int = 1):
+                        idx_offset: int = 0, defer: bool = False, track: bool = True, boost: int = 1,
+                        n_bad: Optional[torch.Tensor] = None):
     """Tensor-core candidates -> exact sequential-fma re-scoring -> best k, with a per-row
     certificate; rows a level cannot certify go to the next level and finally to the "exact"
     kernel, so the keys are bitwise those of mode "exact".
@@ -1021,7 +1027,7 @@ def _topk_keys_rescored(feature: torch.Tensor, feature_bank: torch.Tensor, k: in
         out = torch.empty((B, k), dtype=torch.int64, device=dev)
         return (out, None, None, None) if defer else out
     levels = _cascade_levels(feature_bank, mode, track, boost)
-    out, flags, n_bad = _rescored_level(feature, feature_bank, k, levels[0], idx_offset)
+    out, flags, n_bad = _rescored_level(feature, feature_bank, k, levels[0], idx_offset, n_bad)
 
     def fix(rows, n_rows_bad):
         _note_first_level(feature_bank, mode, levels, B, n_rows_bad, track)
@@ -1067,7 +1073,7 @@ def merge_keys(keys_in: torch.Tensor, k_out: int) -> torch.Tensor:
 
 def vote(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn_t: float,
          label_offset: int = 0, return_scores: bool = False, check_labels: bool = True,
-         return_flag: bool = False):
+         return_flag: bool = False, flag: Optional[torch.Tensor] = None):
     """keys (B,k) + labels (N,) -> (B,C) int64 class ranking (score desc, class asc)."""
     lib = _lib.load()
     _require_cuda("feature_labels", feature_labels)
@@ -1082,7 +1088,8 @@ def vote(keys: torch.Tensor, feature_labels: torch.Tensor, num_classes: int, knn
     scores = torch.empty((B, C), dtype=torch.float64, device=dev) if return_scores else None
     if B:
         with torch.cuda.device(dev):
-            flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+            if flag is None:
+                flag = torch.zeros((1,), dtype=torch.int32, device=dev)
             _lib.check(lib.b200knn_vote(keys.data_ptr(), labels.data_ptr(), B, k, labels.numel(),
                                         label_offset, C, float(knn_t), pred.data_ptr(), _ptr(scores),
                                         flag.data_ptr(), _stream()), "vote")
@@ -1107,16 +1114,18 @@ def _predict_enqueue(feature, feature_bank, feature_labels, num_classes, knn_k, 
     be captured into a CUDA graph): (pred (B,C), status int32[2] = [vote flag, rows to recompute],
     bad_rows (B,) mask/flags, fix).  status[0]: 1 label / 2 neighbour index out of range;
     status[1]: rows a sampled threshold starved, or rows whose re-scoring could not be certified."""
+    # one zeroed status word per call: [vote flag, rows to recompute] — the kernels write into it
+    status = torch.zeros((2,), dtype=torch.int32, device=feature.device)
     if mode in RESCORED_MODES:
-        keys, bad_rows, n_bad, fix = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True,
-                                                         track=track, boost=boost)
+        keys, bad_rows, _, fix = _topk_keys_rescored(feature, feature_bank, knn_k, mode, defer=True,
+                                                     track=track, boost=boost, n_bad=status[1:2])
     else:
         keys = topk_keys(feature, feature_bank, knn_k, mode, repair=False)
         bad_rows = keys[:, -1] == 0
-        n_bad = bad_rows.sum().to(torch.int32).view(1)
+        status[1:2] = bad_rows.sum().to(torch.int32)
         fix = None
-    pred, flag = vote(keys, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True)
-    status = torch.stack([flag.view(()), n_bad.view(()).to(torch.int32)])
+    pred, _ = vote(keys, feature_labels, num_classes, knn_t, check_labels=False, return_flag=True,
+                   flag=status[0:1])
     return pred, status, bad_rows, fix
 
 
