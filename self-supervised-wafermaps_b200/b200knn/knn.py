@@ -904,16 +904,16 @@ def scatter_rows(dst: torch.Tensor, src: torch.Tensor, rows: torch.Tensor, count
 
 
 def local_exact_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str,
-                     idx_offset: int) -> torch.Tensor:
+                     idx_offset: int, n_shards: int = 1) -> torch.Tensor:
     """(B, k+1) int64, nothing synchronises: columns [0, k) the exact top-min(k, N) keys of this bank
-    (zero-padded) from the SECOND level of `mode`'s cascade at its base margin (the last level if
-    there is only one), column k = 1 where that level's certificate failed.  Base margin: a
-    shard holds 1/G of the bank, so its rank gaps are already G times wider than the global ones
-    the first level failed on, and the sub-batch stays cheap (shorter lists, fewer rows to gather)."""
+    shard (zero-padded), column k = 1 where the certificate failed.  One level of `mode`'s cascade at
+    its base margin: a shard holds 1/G of the bank, so its rank gaps are G times wider than the
+    global ones the first level failed on.  With G >= 4 shards the FIRST level (fp16, 1 MMA per
+    k-step) is therefore tried again on the shard; below that the second (fp16 x split-fp16)."""
     B = feature.shape[0]
     N = feature_bank.shape[1]
     levels = _cascade_levels(feature_bank, mode, track=False)
-    level = (levels[1] if len(levels) > 1 else levels[0]).partition("@")[0]
+    level = (levels[0] if n_shards >= 4 or len(levels) == 1 else levels[1]).partition("@")[0]
     k_loc = min(int(k), N)
     out = torch.zeros((B, k + 1), dtype=torch.int64, device=feature.device)
     if B and k_loc:

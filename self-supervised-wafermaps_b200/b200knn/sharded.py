@@ -150,9 +150,9 @@ class _CudaOps:
         return scatter_rows(dst, src, rows, count)
 
     @staticmethod
-    def local_exact_keys(feature, bank_shard, k, mode, idx_offset):
+    def local_exact_keys(feature, bank_shard, k, mode, idx_offset, n_shards=1):
         from .knn import local_exact_keys
-        return local_exact_keys(feature, bank_shard, k, mode, idx_offset)
+        return local_exact_keys(feature, bank_shard, k, mode, idx_offset, n_shards)
 
 
 class ShardedBank:
@@ -494,10 +494,11 @@ class ShardedBank:
         if hasattr(self.ops, "compact_rows"):
             if self._l2_cap is None:
                 self._l2_cap = {}
-            cap = self._l2_cap.get(B) or min(B, max(256, -(-B // 64)))
+            cap = self._l2_cap.get(B) or min(B, max(256, -(-B // 64)))  # first call: 1/64 of the batch
             rows, count = self.ops.compact_rows(out, C, 9, cap)
             sub = feature.index_select(0, rows)
-            loc = self.ops.local_exact_keys(sub, self.bank_shard, knn_k, self.mode, self.lo)   # (cap, k+1)
+            loc = self.ops.local_exact_keys(sub, self.bank_shard, knn_k, self.mode, self.lo,
+                                            self.world_size)                                # (cap, k+1)
             allk = self._gather(loc)                                                        # (G, cap, k+1)
             keys2 = self.ops.merge_keys(allk[:, :, :knn_k].contiguous(), knn_k)
             pk2 = self.ops.vote_packed(keys2, self.labels, C, knn_t, cap)
@@ -515,8 +516,10 @@ class ShardedBank:
         status = out[:, C]
         pred = out[:, :C].contiguous()
         self.last_uncertified = int(host[4]) if n_open is not None else int(((status & 9) != 0).sum().item())
-        if n_open is not None and host[4] > cap:
-            self._l2_cap[B] = min(B, 2 * max(cap, int(host[4])))
+        if n_open is not None:
+            # the second level costs every shard the same whatever G is: size it to ~1.5x the rows
+            # the first level really leaves open (rounded up to 256), at least 256
+            self._l2_cap[B] = min(B, max(256, -(-int(1.5 * host[4]) // 256) * 256))
         if len(levels) > 1:
             from .knn import next_boost
             self._boost, self._calm = next_boost(self._boost, self._calm, B, self.last_uncertified)

@@ -148,7 +148,7 @@ class OracleOps:
         dst[rows[:m]] = src[:m]
 
     @classmethod
-    def local_exact_keys(cls, feature, bank_shard, k, mode, idx_offset):
+    def local_exact_keys(cls, feature, bank_shard, k, mode, idx_offset, n_shards=1):
         B, n = feature.shape[0], bank_shard.shape[1]
         out = torch.zeros((B, k + 1), dtype=torch.int64)
         k_loc = min(k, n)
