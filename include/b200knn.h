@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200KNN_VERSION 140 /* 0.1.4: + b200knn_topk_exact_below (k > 992), b200knn_route_scatter, b200knn_rescore_scatter,
+#define B200KNN_VERSION 141 /* 0.1.4.1: + b200knn_plan_info_ex; 0.1.4: + b200knn_topk_exact_below (k > 992), b200knn_route_scatter, b200knn_rescore_scatter,
                               b200knn_compact_rows, b200knn_scatter_rows (sync-free sharded fp32 mode); 0.1.3: + B200KNN_MODE_F16; 0.1.2: + b200knn_route_keys, b200knn_certify (sharded fp32 mode); 0.1.1: b200knn_rescore workspace */
 
 /* error codes */
@@ -334,6 +334,12 @@ int b200knn_device_ok(void);
 /* How b200knn_topk decomposes a call (for the bench and the docs):
  * out6 = {n_qtiles, splits, split_rows, n_items, grid, list_capacity}. HOST pointer. */
 int b200knn_plan_info(int mode, int64_t B, int64_t N, int dim, int k, int64_t* host_out6);
+/* ... plus the chunk-major order of the tensor-core kernel: out9 = out6 + {chunks, chunk_rows, slots}
+ * (a worker keeps `slots` query tiles open and scans the bank in `chunks` L2-sized pieces). */
+int b200knn_plan_info_ex(int mode, int64_t B, int64_t N, int dim, int k, int64_t* host_out9);
+/* Tuning knob: bytes of bank one chunk of the chunk-major order may occupy (default 40 MiB, or
+ * $B200KNN_L2_CHUNK_MB; 0 = never chunk).  Process-wide; affects planning only, never results. */
+int b200knn_set_l2_chunk_bytes(int64_t bytes);
 
 /* TEST HOOK, not a product entry point: b200knn_topk for the tensor-core modes
  * that also dumps the raw (B,N) fp32 similarity tiles it selected from, and a

@@ -97,6 +97,8 @@ SIGNATURES = {
          ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "b200knn_plan_info": (c_int, [c_int, c_int64, c_int64, c_int, c_int, ctypes.POINTER(c_int64)]),
+    "b200knn_set_l2_chunk_bytes": (c_int, [c_int64]),
+    "b200knn_plan_info_ex": (c_int, [c_int, c_int64, c_int64, c_int, c_int, ctypes.POINTER(c_int64)]),
     "b200knn_debug_topk_dump": (
         c_int,
         [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,

@@ -1290,7 +1290,7 @@ def knn_topk(feature: torch.Tensor, feature_bank: torch.Tensor, k: int,
 
 def plan_info(B: int, N: int, D: int, k: int, mode: Optional[str] = None) -> dict:
     lib = _lib.load()
-    out = (ctypes.c_int64 * 6)()
-    _lib.check(lib.b200knn_plan_info(_lib.MODES[mode or _default_mode], B, N, D, k, out), "plan_info")
-    names = ("n_qtiles", "splits", "split_rows", "n_items", "grid", "list_capacity")
+    out = (ctypes.c_int64 * 9)()
+    _lib.check(lib.b200knn_plan_info_ex(_lib.MODES[mode or _default_mode], B, N, D, k, out), "plan_info")
+    names = ("n_qtiles", "splits", "split_rows", "n_items", "grid", "list_capacity", "chunks", "chunk_rows", "slots")
     return dict(zip(names, [int(v) for v in out]))

@@ -2,6 +2,7 @@
 // Argument validation, work planning, workspace carving, kernel dispatch.
 // No device allocation, no implicit synchronisation, no exceptions.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/b200knn.h"
@@ -34,6 +35,18 @@ bool is_tc_mode(int mode) {
          mode == B200KNN_MODE_F16X2 || mode == B200KNN_MODE_F16;
 }
 
+// Bytes of bank the chunk-major order keeps L2-resident per chunk phase (plan.h).  B200: 126 MB of
+// L2 in two halves; 40 MB leaves room for the query tiles and the list traffic.  B200KNN_L2_CHUNK_MB=0
+// switches chunking off (A/B experiments).
+int64_t g_l2_chunk_bytes = -1;
+int64_t l2_chunk_bytes() {
+  if (g_l2_chunk_bytes < 0) {
+    const char* e = getenv("B200KNN_L2_CHUNK_MB");
+    g_l2_chunk_bytes = (e != nullptr ? atoll(e) : 40) << 20;
+  }
+  return g_l2_chunk_bytes;
+}
+
 bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan* plan) {
   const int cap = b200knn::list_capacity(k);
   if (cap == 0) return false;
@@ -44,7 +57,10 @@ bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan*
   } else {
     // a worker of the tensor-core kernel is one CTA, or a CTA pair owning 256 query rows
     const int pair = b200knn::tc_use_pair(mode, B) ? 2 : 1;
-    *plan = b200knn::make_plan(B, N, k, cap, 128 * pair, b200knn::tc_tile_n(mode, dim), sms / pair);
+    const int64_t d_pad = (dim + 63) / 64 * 64;
+    const int64_t row_bytes = d_pad * (mode == B200KNN_MODE_TF32X3 ? 8 : (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16) ? 2 : 4);
+    *plan = b200knn::make_plan(B, N, k, cap, 128 * pair, b200knn::tc_tile_n(mode, dim), sms / pair, row_bytes,
+                               l2_chunk_bytes());
   }
   return true;
 }
@@ -109,7 +125,10 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
   const size_t slack = ws - reinterpret_cast<uintptr_t>(workspace);
   if (workspace_bytes < plan.total_bytes + slack) return fail(B200KNN_E_WORKSPACE, "topk: workspace too small");
   uint64_t* lists = reinterpret_cast<uint64_t*>(ws);
-  uint64_t* partial = plan.splits > 1 ? reinterpret_cast<uint64_t*>(ws + plan.lists_bytes) : out_keys;
+  float* st_tau = plan.chunks > 1 ? reinterpret_cast<float*>(ws + plan.lists_bytes) : nullptr;
+  uint32_t* st_cnt = plan.chunks > 1 ? reinterpret_cast<uint32_t*>(st_tau + B) : nullptr;
+  uint64_t* partial =
+      plan.splits > 1 ? reinterpret_cast<uint64_t*>(ws + plan.lists_bytes + plan.state_bytes) : out_keys;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (mode == B200KNN_MODE_EXACT) {
@@ -161,6 +180,11 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
     p.n_qtiles = plan.n_qtiles;
     p.n_items = plan.n_items;
     p.split_rows = plan.split_rows;
+    p.n_chunks = plan.chunks;
+    p.slots = plan.slots;
+    p.chunk_rows = plan.chunk_rows;
+    p.st_tau = st_tau;
+    p.st_cnt = st_cnt;
     p.lists = lists;
     p.out = partial;
     p.bank_row_stride = bank_row_stride;
@@ -266,6 +290,22 @@ int b200knn_plan_info(int mode, int64_t B, int64_t N, int dim, int k, int64_t* o
   out6[3] = plan.n_items;
   out6[4] = plan.grid;
   out6[5] = plan.cap;
+  return B200KNN_OK;
+}
+
+int b200knn_set_l2_chunk_bytes(int64_t bytes) {
+  if (bytes < 0) return fail(B200KNN_E_ARG, "set_l2_chunk_bytes: negative");
+  g_l2_chunk_bytes = bytes;
+  return B200KNN_OK;
+}
+
+int b200knn_plan_info_ex(int mode, int64_t B, int64_t N, int dim, int k, int64_t* out9) {
+  b200knn::TopkPlan plan;
+  if (!out9 || !plan_for(mode, B, N, dim, k, &plan)) return fail(B200KNN_E_ARG, "plan_info_ex: bad argument");
+  if (b200knn_plan_info(mode, B, N, dim, k, out9) != B200KNN_OK) return B200KNN_E_ARG;
+  out9[6] = plan.chunks;
+  out9[7] = plan.chunk_rows;
+  out9[8] = plan.slots;
   return B200KNN_OK;
 }
 

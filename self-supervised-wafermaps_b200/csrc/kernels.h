@@ -107,6 +107,10 @@ struct TcParams {
   int D, k;
   int64_t idx_offset;
   int64_t n_qtiles, n_items, split_rows;
+  int n_chunks = 1, slots = 1;  // chunk-major order (plan.h): bank chunks per tile, open tiles per worker
+  int64_t chunk_rows = 0;
+  float* st_tau = nullptr;      // (B,) parked thresholds / list fills between the chunks of a tile
+  uint32_t* st_cnt = nullptr;
   uint64_t* lists;
   uint64_t* out;  // (splits, B, k)
   int64_t bank_row_stride = 1;  // visit every bank_row_stride-th prepared row (sampling pre-pass)

@@ -86,6 +86,16 @@ struct TcKernelArgs {
   int n_stages;
   int64_t idx_offset;
   int64_t n_qtiles, n_items, split_rows;  // n_qtiles counts 128-row tiles (256-row tile pairs when PAIR)
+  // Chunk-major order (n_chunks > 1; only with one bank split): a worker keeps up to `slots` query
+  // tiles "open" at once and scans the bank chunk by chunk — every open tile over chunk 0, then
+  // every open tile over chunk 1, ... — so the chunk being scanned (sized to stay in L2) is read
+  // from HBM once per group of tiles instead of once per tile per drifting worker.  The per-row
+  // selection state (threshold, list fill) of a tile survives between its chunks in st_tau /
+  // st_cnt, its list in the worker's slot of `lists`.
+  int n_chunks, slots;
+  int64_t chunk_rows;
+  float* st_tau;     // (B,)
+  uint32_t* st_cnt;  // (B,)
   uint64_t* lists;
   uint64_t* out;
   const float* tau0;  // optional (B,) initial admission thresholds (nullptr: -inf)
@@ -116,6 +126,44 @@ struct TcKernelArgs {
 // insert — no candidate lists, no prunes, no indices.  Its 16-th value is <= the 16-th best
 // sampled similarity, which is all the main pass's admission threshold needs.  The general
 // list machinery spent 2/3 of the pre-pass warming up its lists.
+// One unit of work of a worker: query tile `qt` against bank rows [n_begin, n_end).
+struct WorkItem {
+  int64_t qt, sp, n_begin, n_end;
+  int slot;          // which of the worker's list slots the tile's lists live in
+  bool first, last;  // first / last visit of this tile (start from tau0 / flush the result)
+};
+
+// The sequence of work items of `worker` — identical for the producer, the MMA issuer and the
+// epilogue warps, which is what keeps their barrier phases aligned.
+template <typename F>
+__device__ __forceinline__ void for_each_item(const TcKernelArgs& a, int64_t worker, int64_t n_workers, F&& body) {
+  // Items are numbered split-major (item = sp * n_qtiles + qt) and dealt round-robin to the
+  // workers, so concurrently running workers stream the same bank split.  Without chunks
+  // (n_chunks == 1, slots == 1, chunk_rows == split_rows) this is one pass over the worker's items;
+  // with chunks (one split only) the worker's tiles are taken in groups of `slots`, each group
+  // scanned chunk by chunk.  ONE call site of `body` (it is large and must not be duplicated).
+  const int64_t n_units = worker < a.n_items ? (a.n_items - worker + n_workers - 1) / n_workers : 0;
+  WorkItem it;
+  for (int64_t g0 = 0; g0 < n_units; g0 += a.slots) {
+    const int glen = int(n_units - g0 < a.slots ? n_units - g0 : a.slots);
+    for (int c = 0; c < a.n_chunks; ++c) {
+      it.first = (c == 0);
+      it.last = (c == a.n_chunks - 1);
+      for (int j = 0; j < glen; ++j) {
+        const int64_t item = worker + (g0 + j) * n_workers;
+        it.qt = item % a.n_qtiles;
+        it.sp = item / a.n_qtiles;
+        const int64_t base = it.sp * a.split_rows;
+        const int64_t span_end = (base + a.split_rows < a.N) ? base + a.split_rows : a.N;
+        it.n_begin = base + int64_t(c) * a.chunk_rows;
+        it.n_end = (it.n_begin + a.chunk_rows < span_end) ? it.n_begin + a.chunk_rows : span_end;
+        it.slot = j;
+        body(it);
+      }
+    }
+  }
+}
+
 template <int MODE, int BLOCK_N, int ITEMS, bool DEBUG, bool PAIR, bool SAMPLE>
 __global__ void __launch_bounds__(kThreads, 1)
     tc_topk_kernel(const __grid_constant__ CUtensorMap map_q_hi,
@@ -195,11 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       int stage = 0;
       uint32_t phase = 0, q_phase = 0;
       const uint32_t qbar = PAIR ? ptx::mapa(ptx::smem_u32(&bars->q_full), 0) : ptx::smem_u32(&bars->q_full);
-      for (int64_t item = worker; item < a.n_items; item += n_workers) {
-        const int64_t qt = item % a.n_qtiles, sp = item / a.n_qtiles;
-        const int m0 = int((qt * kCtas + cta_rank) * kTileM);
-        const int64_t n_begin = sp * a.split_rows;
-        const int64_t n_end = (n_begin + a.split_rows < a.N) ? n_begin + a.split_rows : a.N;
+      for_each_item(a, worker, n_workers, [&](const WorkItem& it) {
+        const int m0 = int((it.qt * kCtas + cta_rank) * kTileM);
+        const int64_t n_begin = it.n_begin, n_end = it.n_end;
         if (kBf16) {
           ptx::mbar_wait(ptx::smem_u32(&bars->q_empty), q_phase ^ 1, a.diag, 1);
           if (ptx::elect_one()) {
@@ -250,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
         }
-      }
+      });
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
@@ -262,10 +308,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t tcount = 0;
       const uint64_t desc0 = ptx::smem_desc_sw128(0);
       const uint32_t q_base = ptx::smem_u32(q_smem), st_base = ptx::smem_u32(stage_smem);
-      for (int64_t item = worker; item < a.n_items; item += n_workers) {
-        const int64_t sp = item / a.n_qtiles;
-        const int64_t n_begin = sp * a.split_rows;
-        const int64_t n_end = (n_begin + a.split_rows < a.N) ? n_begin + a.split_rows : a.N;
+      for_each_item(a, worker, n_workers, [&](const WorkItem& it) {
+        const int64_t n_begin = it.n_begin, n_end = it.n_end;
         if (kBf16) {
           ptx::mbar_wait(ptx::smem_u32(&bars->q_full), q_phase, a.diag, 3);
           q_phase ^= 1;
@@ -335,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           __syncwarp();
         }
-      }
+      });
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -343,8 +387,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int sub = (warp - 2) / 4;           // which of the quarter's warps
     const bool owner = (lane / kRowsPerWarp) == sub;  // this lane's row is selected by this warp
     const int row_in_tile = quarter * 32 + lane;
-    uint64_t* warp_lists = a.lists + (size_t(blockIdx.x) * kTileM + size_t(quarter) * 32) * CAP;
-    uint64_t* my_list = warp_lists + size_t(lane) * CAP;
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
     // the barrier the MMA thread waits on before overwriting an accumulator buffer
@@ -355,15 +397,23 @@ __global__ void __launch_bounds__(kThreads, 1)
     // free slots below which a row is pruned between tiles (off the critical path)
     const int soft_slack = min(96, (CAP - a.k) / 2);
     uint32_t tcount = 0;
-    for (int64_t item = worker; item < a.n_items; item += n_workers) {
-      const int64_t qt = item % a.n_qtiles, sp = item / a.n_qtiles;
-      const int64_t m0 = (qt * kCtas + cta_rank) * kTileM;
-      const int64_t n_begin = sp * a.split_rows;
-      const int64_t n_end = (n_begin + a.split_rows < a.N) ? n_begin + a.split_rows : a.N;
+    for_each_item(a, worker, n_workers, [&](const WorkItem& it) {
+      const int64_t sp = it.sp;
+      const int64_t m0 = (it.qt * kCtas + cta_rank) * kTileM;
+      const int64_t n_begin = it.n_begin, n_end = it.n_end;
       const int64_t grow = m0 + row_in_tile;
+      uint64_t* warp_lists =
+          a.lists + ((size_t(blockIdx.x) * size_t(a.slots) + size_t(it.slot)) * kTileM + size_t(quarter) * 32) * CAP;
+      uint64_t* my_list = warp_lists + size_t(lane) * CAP;
+      const bool mine = owner && grow < a.B;  // this lane selects for a real query row
       RowState st;
-      st.cnt = 0;
-      st.tau = (owner && grow < a.B) ? (a.tau0 != nullptr ? a.tau0[grow] : neg_inf) : pos_inf;
+      if (it.first || SAMPLE) {
+        st.cnt = 0;
+        st.tau = mine ? (a.tau0 != nullptr ? a.tau0[grow] : neg_inf) : pos_inf;
+      } else {  // resume this tile where its previous chunk left it
+        st.cnt = mine ? a.st_cnt[grow] : 0u;
+        st.tau = mine ? a.st_tau[grow] : pos_inf;
+      }
       float top[SAMPLE ? kSampleR : 1];  // SAMPLE: this row's best similarities, descending
 #pragma unroll
       for (int i = 0; i < (SAMPLE ? kSampleR : 1); ++i) top[i] = neg_inf;
@@ -482,7 +532,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int i = 0; i < kSampleR; ++i) o[i] = top[i] > neg_inf ? make_key(top[i], 0u) : 0ull;
         }
-        continue;
+        return;
+      }
+      if (!it.last) {  // more chunks of this tile to come: park the selection state
+        if (mine) {
+          a.st_cnt[grow] = st.cnt;
+          a.st_tau[grow] = st.tau;
+        }
+        __syncwarp();  // this lane's list appends are read by the whole warp's prunes later
+        return;
       }
       const int64_t row0 = m0 + quarter * 32;
       unsigned valid = 0;
@@ -500,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         return a.out + (size_t(sp) * a.B + size_t(g)) * a.k;
       });
-    }
+    });
   }
 
   ptx::tc_fence_before();
@@ -570,6 +628,12 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   a.n_qtiles = p.n_qtiles;
   a.n_items = p.n_items;
   a.split_rows = p.split_rows;
+  // the sampling variant keeps its row state in registers: always one chunk
+  a.n_chunks = (SAMPLE || p.n_chunks < 1) ? 1 : p.n_chunks;
+  a.slots = (SAMPLE || p.slots < 1) ? 1 : p.slots;
+  a.chunk_rows = a.n_chunks > 1 ? p.chunk_rows : p.split_rows;
+  a.st_tau = p.st_tau;
+  a.st_cnt = p.st_cnt;
   a.lists = p.lists;
   a.out = p.out;
   a.tau0 = p.tau0;

@@ -362,3 +362,36 @@ def test_from_batches_preallocated_buffer():
         fb = b200knn.FeatureBank.from_batches(chunks, total_rows=total)
         assert fb.n_rows == 1000 and fb.rows.is_contiguous()
         assert torch.equal(fb.rows, ref.rows) and torch.equal(fb.labels, ref.labels)
+
+
+# ------------------------------------------------------------------ chunk-major order of the tensor-core kernel
+@pytest.mark.parametrize("mode,k", [("bf16", 50), ("f16", 50), ("f16x2", 50), ("bf16x3", 50), ("tf32x3", 50), ("fp32", 50),
+                                    ("f16", 200), ("fp32", 200)])
+def test_chunk_major_order_does_not_change_results(mode, k):
+    """With several query tiles per worker the kernel scans the bank chunk by chunk, parking every
+    row's threshold and list fill between the chunks of its tile.  Keys must be bitwise those of
+    the single-pass order (chunking off), for ragged chunk / tile / batch ends and k near the list
+    capacity; fp32 must equal the exact mode."""
+    from b200knn import _lib
+
+    lib = _lib.load()
+    D, N, B = 128, 20011, 37883
+    g = torch.Generator(device=DEV).manual_seed(77)
+    bank = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device=DEV), dim=1).t().contiguous()
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device=DEV), dim=1)
+    raw = K.RESCORED_MODES[mode]["cand"] if mode in K.RESCORED_MODES else mode
+    try:
+        assert lib.b200knn_set_l2_chunk_bytes(0) == 0
+        assert K.plan_info(B, N, D, k, raw)["chunks"] == 1
+        one_pass = b200knn.topk_keys(q, bank, k, mode=mode)
+        for chunk_bytes in (1 << 20, 300 << 10):
+            assert lib.b200knn_set_l2_chunk_bytes(chunk_bytes) == 0
+            plan = K.plan_info(B, N, D, k + (K.RESCORED_MODES[mode]["margin"] if mode in K.RESCORED_MODES else 0), raw)
+            assert plan["chunks"] > 1 and plan["slots"] > 1 and plan["splits"] == 1, plan
+            chunked = b200knn.topk_keys(q, bank, k, mode=mode)
+            assert torch.equal(chunked, one_pass), (mode, plan)
+        if mode == "fp32":
+            sample = torch.arange(0, B, 97, device=DEV)
+            assert torch.equal(chunked[sample], b200knn.topk_keys(q[sample].contiguous(), bank, k, mode="exact"))
+    finally:
+        lib.b200knn_set_l2_chunk_bytes(40 << 20)
