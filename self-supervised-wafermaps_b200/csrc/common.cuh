@@ -147,28 +147,35 @@ __device__ __forceinline__ float warp_prune_select(uint64_t* list, int n_valid, 
   }
   all_and = __reduce_and_sync(kFull, all_and);
   all_or = __reduce_or_sync(kFull, all_or);
-  // bits on which all sims agree are fixed; search the others from the most significant down
-  uint32_t T = all_and;
-  uint32_t open_bits = all_and ^ all_or;
-  while (open_bits) {
-    const uint32_t bit = 0x80000000u >> __clz(open_bits);
-    open_bits &= ~bit;
-    const uint32_t cand = T | bit;
-    int c = 0;
-#pragma unroll
-    for (int r = 0; r < ITEMS; ++r) c += (hi[r] >= cand) ? 1 : 0;
-    c = __reduce_add_sync(kFull, c);
-    if (c >= k) T = cand;
-  }
-  // now count(hi >= T) >= k and count(hi > T) < k
-  int c = 0;
-#pragma unroll
-  for (int r = 0; r < ITEMS; ++r) c += (hi[r] >= T) ? 1 : 0;
-  c = __reduce_add_sync(kFull, c);
   // Every caller may append up to 32 more keys before it checks the list again, so the kept
   // count must also leave 32 free slots (k close to CAP: one tie at the cut would otherwise let
   // the next chunk of appends run past the list).
   const int room = (k + (CAP - k) / 4 < CAP - 32) ? k + (CAP - k) / 4 : CAP - 32;
+  // bits on which all sims agree are fixed; search the others from the most significant down.
+  // The search stops as soon as the count above the candidate threshold lies in [k, room]: the
+  // threshold need not be the exact k-th similarity, any value that keeps between k and `room`
+  // keys is as good (a few extra keys survive until the next prune / the final sort).  That
+  // ends the search after the few bits that separate ~CAP values down to a window of room - k,
+  // instead of walking all ~22 open mantissa bits — prunes sit on the accumulator hand-over's
+  // critical path (one late warp of 16 stalls the MMA issuer), so their latency is what matters.
+  uint32_t T = all_and;
+  uint32_t open_bits = all_and ^ all_or;
+  int c = n_valid;  // keys with hi >= T
+  while (open_bits) {
+    const uint32_t bit = 0x80000000u >> __clz(open_bits);
+    open_bits &= ~bit;
+    const uint32_t cand = T | bit;
+    int cc = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) cc += (hi[r] >= cand) ? 1 : 0;
+    cc = __reduce_add_sync(kFull, cc);
+    if (cc >= k) {
+      T = cand;
+      c = cc;
+      if (c <= room) break;
+    }
+  }
+  // now count(hi >= T) = c >= k (n_valid >= k is the caller's precondition); ties at T are all kept
   if (c > room) {
     *kept = -1;
     return 0.0f;

@@ -8,7 +8,15 @@
 
 namespace b200knn {
 
+// Bank rows per accumulator tile.  The resident-query modes can run 256-wide tiles (2 TMEM
+// buffers) up to D_pad = 512; B200KNN_TILE_N=128 forces 128-wide tiles (4 TMEM buffers) for A/B runs.
 int tc_tile_n(int mode, int dim) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("B200KNN_TILE_N");
+    forced = (e != nullptr && atoi(e) == 128) ? 128 : 0;
+  }
+  if (forced == 128) return 128;
   if (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16X2 || mode == B200KNN_MODE_F16)
     return ((dim + 63) / 64 * 64) <= 512 ? 256 : 128;
   return 128;

@@ -54,7 +54,8 @@ namespace b200knn {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
+constexpr int kMaxAccBufs = 4;  // TMEM accumulator buffers: 512 columns / BLOCK_N
 constexpr int kRowBytes = 128;                   // one swizzle row = one k-block of a vector
 constexpr int kABlockBytes = kTileM * kRowBytes;  // 16 KB: 128 query rows x one k-block
 #ifndef B200KNN_EPI_PER_QUARTER
@@ -71,8 +72,8 @@ constexpr int kSampleR = 16;        // values kept per row by the SAMPLE variant
 struct alignas(16) Barriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[kMaxAccBufs];
+  uint64_t tmem_empty[kMaxAccBufs];
   uint64_t q_full;
   uint64_t q_empty;
   uint32_t tmem_base;
@@ -192,7 +193,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr uint32_t kIdesc =
       ptx::make_idesc((MODE == B200KNN_MODE_F16X2 || MODE == B200KNN_MODE_F16) ? 0u : (kHalf ? 1u : 2u),
                       kTileM * kCtas, BLOCK_N);
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+  // all 512 TMEM columns: 2 accumulator buffers of 256 columns, or 4 of 128.  More buffers let the
+  // MMA issuer run further ahead of the slowest of the 16 epilogue warps it hands tiles to (a warp
+  // that prunes a list is late for a whole tile time).
+  constexpr int kAccBufs = 512 / BLOCK_N;
+  static_assert(kAccBufs >= 2 && kAccBufs <= kMaxAccBufs, "BLOCK_N must be 128 or 256");
+  constexpr uint32_t kTmemCols = 512;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::mbar_init(ptx::smem_u32(&bars->full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->empty[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAccBufs; ++b) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[b]), 1);
       // one arrive per epilogue warp (of both CTAs of a pair: the leader's barrier collects them)
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[b]), kEpiWarps * kCtas);
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           q_phase ^= 1;
         }
         for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
-          const uint32_t buf = tcount & 1u, aphase = (tcount >> 1) & 1u;
+          const uint32_t buf = tcount % kAccBufs, aphase = (tcount / kAccBufs) & 1u;
           ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[buf]), aphase ^ 1, a.diag, 4);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
@@ -406,8 +412,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     // the barrier the MMA thread waits on before overwriting an accumulator buffer
     const uint32_t tmem_empty_bar0 = PAIR ? ptx::mapa(ptx::smem_u32(&bars->tmem_empty[0]), 0)
                                           : ptx::smem_u32(&bars->tmem_empty[0]);
-    const uint32_t tmem_empty_bar1 = PAIR ? ptx::mapa(ptx::smem_u32(&bars->tmem_empty[1]), 0)
-                                          : ptx::smem_u32(&bars->tmem_empty[1]);
     // free slots below which a row is pruned between tiles (off the critical path)
     const int soft_slack = min(96, (CAP - a.k) / 2);
     uint32_t tcount = 0;
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int i = 0; i < (SAMPLE ? kSampleR : 1); ++i) top[i] = neg_inf;
       for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
-        const uint32_t buf = tcount & 1u, aphase = (tcount >> 1) & 1u;
+        const uint32_t buf = tcount % kAccBufs, aphase = (tcount / kAccBufs) & 1u;
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[buf]), aphase, a.diag, 6);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BLOCK_N;
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              const uint32_t bar = buf ? tmem_empty_bar1 : tmem_empty_bar0;
+              const uint32_t bar = tmem_empty_bar0 + buf * uint32_t(sizeof(uint64_t));  // same offset in the leader's smem
               if (PAIR) ptx::mbar_arrive_cluster(bar);
               else ptx::mbar_arrive(bar);
             }
