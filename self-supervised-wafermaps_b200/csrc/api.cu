@@ -60,7 +60,7 @@ bool plan_for(int mode, int64_t B, int64_t N, int dim, int k, b200knn::TopkPlan*
     const int64_t d_pad = (dim + 63) / 64 * 64;
     const int64_t row_bytes = d_pad * (mode == B200KNN_MODE_TF32X3 ? 8 : (mode == B200KNN_MODE_BF16 || mode == B200KNN_MODE_F16) ? 2 : 4);
     *plan = b200knn::make_plan(B, N, k, cap, 128 * pair, b200knn::tc_tile_n(mode, dim), sms / pair, row_bytes,
-                               l2_chunk_bytes(), 2, B200KNN_SAMPLE_R);
+                               l2_chunk_bytes());
   }
   return true;
 }
@@ -125,14 +125,10 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
   const size_t slack = ws - reinterpret_cast<uintptr_t>(workspace);
   if (workspace_bytes < plan.total_bytes + slack) return fail(B200KNN_E_WORKSPACE, "topk: workspace too small");
   uint64_t* lists = reinterpret_cast<uint64_t*>(ws);
-  // parked row state of the chunk-major order: (2, B) thresholds then (2, B) list fills (tensor-core kernel)
   float* st_tau = plan.chunks > 1 ? reinterpret_cast<float*>(ws + plan.lists_bytes) : nullptr;
-  uint32_t* st_cnt = plan.chunks > 1 ? reinterpret_cast<uint32_t*>(st_tau + 2 * B) : nullptr;
-  // the sampling variant writes one list per column half and split: always merged (2 * splits lists)
-  const int n_partial = sample ? 2 * plan.splits : plan.splits;
-  if (sample && plan.partial_bytes == 0) return fail(B200KNN_E_ARG, "topk_sample: k must be B200KNN_SAMPLE_R");
+  uint32_t* st_cnt = plan.chunks > 1 ? reinterpret_cast<uint32_t*>(st_tau + B) : nullptr;
   uint64_t* partial =
-      n_partial > 1 ? reinterpret_cast<uint64_t*>(ws + plan.lists_bytes + plan.state_bytes) : out_keys;
+      plan.splits > 1 ? reinterpret_cast<uint64_t*>(ws + plan.lists_bytes + plan.state_bytes) : out_keys;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (mode == B200KNN_MODE_EXACT) {
@@ -209,8 +205,8 @@ static int topk_impl(int mode, const void* q_hi, const void* q_lo, int q_dtype, 
   } else {
     return fail(B200KNN_E_ARG, "topk: unknown mode");
   }
-  if (n_partial > 1) {
-    e = b200knn::launch_merge(partial, n_partial, B, k, k, out_keys, st);
+  if (plan.splits > 1) {
+    e = b200knn::launch_merge(partial, plan.splits, B, k, k, out_keys, st);
     if (e != cudaSuccess) return fail_cuda("topk(merge)", e);
   }
   return B200KNN_OK;

@@ -284,71 +284,4 @@ __device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, 
   __syncwarp();
 }
 
-// Sort the concatenation of the first nA keys of A and the first nB keys of B (nA + nB <= S*32)
-// descending and write the best k to `o` (zero-padded).
-template <int S>
-__device__ __forceinline__ void sort_store_two(const uint64_t* A, int nA, const uint64_t* B, int nB, int k,
-                                               int lane, uint64_t* o) {
-  uint64_t v[S];
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-    const int i = r * 32 + lane;
-    v[r] = (i < nA) ? A[i] : ((i < nA + nB) ? B[i - nA] : 0ull);
-  }
-  warp_sort_desc<S>(v, lane);
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-    const int i = r * 32 + lane;
-    if (i < k) o[i] = v[r];
-  }
-  for (int i = S * 32 + lane; i < k; i += 32) o[i] = 0ull;
-}
-
-// End of a work item of the tensor-core kernel, whose two epilogue warps per lane quarter each
-// kept their own list per row (one per column half): for every row r in valid_mask the union of
-// listsA[r] (cntA[r] keys) and listsB[r] (cntB[r] keys) is cut to its best k, sorted and written to
-// out_of(r).  Each sublist is first cut to ~k on its own (the union of the two top-k's holds the
-// row's top-k): radix-select, or the exact sort when ties defeat it; 2k + 32 <= CAP by the
-// capacity rule, so the union then fits one sorting network sized to what is left.
-template <int ITEMS, typename OutFn>
-__device__ __forceinline__ void warp_flush2(uint64_t* listsA, uint64_t* listsB, const uint32_t* cntA,
-                                            const uint32_t* cntB, int k, int lane, unsigned valid_mask,
-                                            OutFn out_of) {
-  constexpr int CAP = ITEMS * 32;
-  for (int src = 0; src < 32; ++src) {
-    if (!((valid_mask >> src) & 1u)) continue;
-    uint64_t* A = listsA + size_t(src) * CAP;
-    uint64_t* B = listsB + size_t(src) * CAP;
-    int n[2] = {int(cntA[src]), int(cntB[src])};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint64_t* L = h ? B : A;
-      if (n[h] > k && (n[0] + n[1] > CAP || n[h] > 256)) {
-        int kept = -1;
-        warp_prune_select<ITEMS>(L, n[h], k, lane, &kept);
-        if (kept >= 0) n[h] = kept;
-        __syncwarp();
-      }
-    }
-    if (n[0] + n[1] > CAP) {  // ties kept by the select: cut exactly (sorted, index order breaks the ties)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (n[h] > k) {
-          warp_prune<ITEMS>(h ? B : A, n[h], k, lane);
-          n[h] = k;
-          __syncwarp();
-        }
-      }
-    }
-    uint64_t* o = out_of(src);
-    const int tot = n[0] + n[1];
-    if (tot <= 64) sort_store_two<2>(A, n[0], B, n[1], k, lane, o);
-    else if (ITEMS >= 4 && tot <= 128) sort_store_two<(ITEMS >= 4 ? 4 : ITEMS)>(A, n[0], B, n[1], k, lane, o);
-    else if (ITEMS >= 8 && tot <= 256) sort_store_two<(ITEMS >= 8 ? 8 : ITEMS)>(A, n[0], B, n[1], k, lane, o);
-    else if (ITEMS >= 16 && tot <= 512) sort_store_two<(ITEMS >= 16 ? 16 : ITEMS)>(A, n[0], B, n[1], k, lane, o);
-    else sort_store_two<ITEMS>(A, n[0], B, n[1], k, lane, o);
-  }
-  __syncwarp();
-}
-
 }  // namespace b200knn

@@ -26,8 +26,8 @@ struct TopkPlan {
   int chunks = 1;
   int slots = 1;
   int64_t chunk_rows = 0;
-  size_t lists_bytes = 0;   // grid * slots * lists_per_row * tile_m * cap * 8
-  size_t state_bytes = 0;   // chunks>1 ? B * 8 * lists_per_row (parked threshold + list fill per list) : 0
+  size_t lists_bytes = 0;   // grid * slots * tile_m * cap * 8
+  size_t state_bytes = 0;   // chunks>1 ? B * 8 (parked threshold + list fill per row) : 0
   size_t partial_bytes = 0; // splits>1 ? splits * B * k * 8 : 0
   size_t total_bytes = 0;
 };
@@ -38,13 +38,8 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Chunking parameters: bytes one bank row occupies in the streamed operand arrays, and the bytes
 // of bank that should stay L2-resident during a chunk phase (0: never chunk).
 constexpr int kMaxSlots = 16;
-// lists_per_row: candidate lists per query row and worker slot (the tensor-core kernel keeps one per
-// column-half warp, the exact kernel one).  sample_k: the k of the sampling variant, which writes
-// one top-sample_k per column half and split — its partial buffer holds 2 * splits lists per row
-// and is always merged.
 inline TopkPlan make_plan(int64_t B, int64_t N, int k, int cap, int tile_m, int tile_n, int ctas,
-                          int64_t bank_row_bytes = 0, int64_t l2_chunk_bytes = 0, int lists_per_row = 1,
-                          int sample_k = 0) {
+                          int64_t bank_row_bytes = 0, int64_t l2_chunk_bytes = 0) {
   TopkPlan p;
   p.tile_m = tile_m;
   p.tile_n = tile_n;
@@ -96,12 +91,9 @@ inline TopkPlan make_plan(int64_t B, int64_t N, int k, int cap, int tile_m, int 
       p.chunk_rows = p.split_rows;
     }
   }
-  p.lists_bytes = align_up(size_t(p.grid) * p.slots * lists_per_row * tile_m * cap * 8, 256);
-  p.state_bytes = p.chunks > 1 ? align_up(size_t(B) * 8 * lists_per_row, 256) : 0;
-  const bool sample_layout = (sample_k > 0 && k == sample_k && lists_per_row > 1);
-  p.partial_bytes = (p.splits > 1 || sample_layout)
-                        ? align_up(size_t(p.splits) * (sample_layout ? lists_per_row : 1) * B * k * 8, 256)
-                        : 0;
+  p.lists_bytes = align_up(size_t(p.grid) * p.slots * tile_m * cap * 8, 256);
+  p.state_bytes = p.chunks > 1 ? align_up(size_t(B) * 8, 256) : 0;
+  p.partial_bytes = p.splits > 1 ? align_up(size_t(p.splits) * B * k * 8, 256) : 0;
   p.total_bytes = p.lists_bytes + p.state_bytes + p.partial_bytes;
   return p;
 }

@@ -78,14 +78,7 @@ struct alignas(16) Barriers {
   uint64_t q_empty;
   uint32_t tmem_base;
   uint32_t pad;
-  uint32_t xcnt[2][kTileM];  // list fills of the two column-half warps of every row, exchanged for the flush
 };
-static_assert(kEpiPerQuarter == 2, "the epilogue splits every accumulator tile between two warps per lane quarter");
-
-// bar.sync on a named barrier: the two epilogue warps of one TMEM lane quarter (64 threads)
-__device__ __forceinline__ void quarter_sync(int quarter) {
-  asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-}
 
 struct TcKernelArgs {
   int64_t B, N;
@@ -396,17 +389,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    // Two warps per TMEM lane quarter.  Each handles ALL 32 rows of the quarter for HALF of the
-    // columns of every accumulator tile (warp 0: columns [0, BLOCK_N/2), warp 1: the rest), with its
-    // own candidate list and threshold per row: no shared state, no atomics while scanning.  A chunk
-    // visit costs the same whether 1 or 32 rows of the warp have a candidate, so halving the visits
-    // per warp (instead of halving the rows, round 1: every warp loaded every chunk and used 16 of
-    // its 32 lanes) removes the duplicated loads / maxima and about a third of the candidate-path
-    // executions.  The two sublists of a row are merged when the tile is flushed.
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int sub = (warp - 2) / 4;           // which column half
+    const int sub = (warp - 2) / 4;           // which of the quarter's warps
+    const bool owner = (lane / kRowsPerWarp) == sub;  // this lane's row is selected by this warp
     const int row_in_tile = quarter * 32 + lane;
-    constexpr int kHalfN = BLOCK_N / 2;
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
     // the barrier the MMA thread waits on before overwriting an accumulator buffer
@@ -420,18 +406,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t m0 = (it.qt * kCtas + cta_rank) * kTileM;
       const int64_t n_begin = it.n_begin, n_end = it.n_end;
       const int64_t grow = m0 + row_in_tile;
-      // lists: [CTA][slot][column half][128 rows][CAP]
-      uint64_t* slot_lists = a.lists + (size_t(blockIdx.x) * size_t(a.slots) + size_t(it.slot)) * 2 * kTileM * CAP;
-      uint64_t* warp_lists = slot_lists + (size_t(sub) * kTileM + size_t(quarter) * 32) * CAP;
+      uint64_t* warp_lists =
+          a.lists + ((size_t(blockIdx.x) * size_t(a.slots) + size_t(it.slot)) * kTileM + size_t(quarter) * 32) * CAP;
       uint64_t* my_list = warp_lists + size_t(lane) * CAP;
-      const bool mine = grow < a.B;  // this lane selects for a real query row
+      const bool mine = owner && grow < a.B;  // this lane selects for a real query row
       RowState st;
       if (it.first || SAMPLE) {
         st.cnt = 0;
         st.tau = mine ? (a.tau0 != nullptr ? a.tau0[grow] : neg_inf) : pos_inf;
       } else {  // resume this tile where its previous chunk left it
-        st.cnt = mine ? a.st_cnt[int64_t(sub) * a.B + grow] : 0u;
-        st.tau = mine ? a.st_tau[int64_t(sub) * a.B + grow] : pos_inf;
+        st.cnt = mine ? a.st_cnt[grow] : 0u;
+        st.tau = mine ? a.st_tau[grow] : pos_inf;
       }
       float top[SAMPLE ? kSampleR : 1];  // SAMPLE: this row's best similarities, descending
 #pragma unroll
@@ -442,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BLOCK_N;
 #pragma unroll 1
-        for (int c0 = sub * kHalfN; c0 < (sub + 1) * kHalfN; c0 += 32) {
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           float s[32];
           if (DEBUG && (a.flags & 2)) {
 #pragma unroll
@@ -450,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           } else {
             ptx::tmem_ld32(taddr + c0, s);
           }
-          if (c0 + 32 == (sub + 1) * kHalfN) {
+          if (c0 + 32 == BLOCK_N) {
             // all of this warp's TMEM reads of the buffer are done: hand it back
             ptx::tc_fence_before();
             __syncwarp();
@@ -460,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               else ptx::mbar_arrive(bar);
             }
           }
-          if (DEBUG && a.dump != nullptr && mine) {
+          if (DEBUG && a.dump != nullptr && owner && grow < a.B) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int64_t gn = n0 + c0 + j;
@@ -546,8 +531,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         ++tcount;
       }
       if (SAMPLE) {
-        if (mine) {  // one top-16 per column half: the host merges 2 * splits lists per row
-          uint64_t* o = a.out + ((size_t(sp) * 2 + size_t(sub)) * a.B + grow) * kSampleR;
+        if (owner && grow < a.B) {
+          uint64_t* o = a.out + (size_t(sp) * a.B + grow) * kSampleR;
 #pragma unroll
           for (int i = 0; i < kSampleR; ++i) o[i] = top[i] > neg_inf ? make_key(top[i], 0u) : 0ull;
         }
@@ -555,26 +540,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if (!it.last) {  // more chunks of this tile to come: park the selection state
         if (mine) {
-          a.st_cnt[int64_t(sub) * a.B + grow] = st.cnt;
-          a.st_tau[int64_t(sub) * a.B + grow] = st.tau;
+          a.st_cnt[grow] = st.cnt;
+          a.st_tau[grow] = st.tau;
         }
         __syncwarp();  // this lane's list appends are read by the whole warp's prunes later
         return;
       }
-      // Flush: the two column-half warps exchange their list fills, then each merges and writes
-      // 16 of the quarter's 32 rows (both sublists of a row: cut to ~k each, sorted together).
-      bars->xcnt[sub][row_in_tile] = st.cnt;
-      quarter_sync(quarter);  // fills + every list append of both warps visible to both
       const int64_t row0 = m0 + quarter * 32;
       unsigned valid = 0;
       if (row0 < a.B) {
         const int64_t nv = a.B - row0;
         valid = nv >= 32 ? kFull : ((1u << nv) - 1u);
       }
-      valid &= 0xffffu << (sub * 16);
-      warp_flush2<ITEMS>(slot_lists + size_t(quarter) * 32 * CAP, slot_lists + (size_t(kTileM) + size_t(quarter) * 32) * CAP,
-                         &bars->xcnt[0][quarter * 32], &bars->xcnt[1][quarter * 32], a.k, lane, valid,
-                         [&](int r) -> uint64_t* {
+      valid &= (kRowsPerWarp == 32 ? kFull : ((1u << kRowsPerWarp) - 1u)) << (sub * kRowsPerWarp);
+      warp_flush<ITEMS>(warp_lists, st, a.k, lane, valid, [&](int r) -> uint64_t* {
         const int64_t g = row0 + r;
         if (a.n_peers > 0) {
           const int64_t owner = g / a.rows_per_owner;
@@ -583,7 +562,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         return a.out + (size_t(sp) * a.B + size_t(g)) * a.k;
       });
-      quarter_sync(quarter);  // nobody reuses the lists / fills for the next item before both are done
     });
   }
 
