@@ -234,31 +234,6 @@ __device__ __forceinline__ void warp_maintain(uint64_t* lists, RowState& st, int
   __syncwarp();
 }
 
-// Opportunistic variant for idle time (a warp waiting for its next accumulator tile): prune ONE
-// row whose list holds more than min_cnt keys, if there is one.  Returns whether it did.
-template <int ITEMS>
-__device__ __forceinline__ bool warp_maintain_one(uint64_t* lists, RowState& st, int k, int lane,
-                                                  int min_cnt) {
-  constexpr int CAP = ITEMS * 32;
-  const unsigned m = __ballot_sync(kFull, int(st.cnt) > min_cnt);
-  if (m == 0) return false;
-  __syncwarp();  // owner's appends visible to the whole warp
-  const int src = __ffs(m) - 1;
-  const int n_valid = __shfl_sync(kFull, int(st.cnt), src);
-  int kept = -1;
-  float t = warp_prune_select<ITEMS>(lists + size_t(src) * CAP, n_valid, k, lane, &kept);
-  if (kept < 0) {
-    t = warp_prune<ITEMS>(lists + size_t(src) * CAP, n_valid, k, lane);
-    kept = n_valid < k ? n_valid : k;
-  }
-  if (lane == src) {
-    st.tau = fmaxf(st.tau, t);
-    st.cnt = uint32_t(kept);
-  }
-  __syncwarp();
-  return true;
-}
-
 // Sort the first n (<= S*32) keys of `list` descending and write the best k to `o`
 // (zero-padded).
 template <int S>

@@ -106,7 +106,6 @@ struct TcKernelArgs {
   uint64_t* peer_out[kMaxPeers];
   int n_peers, my_rank;
   int64_t rows_per_owner;
-  int idle_prune;  // 1: prune grown lists while waiting for the next accumulator tile (B200KNN_IDLE_PRUNE=0: off)
   float* dump;  // optional (B, N) fp32 similarity dump for unit tests (nullptr in production)
   int32_t* diag;
   int flags;    // experiment switches of the debug entry point (0 in production):
@@ -401,9 +400,6 @@ __global__ void __launch_bounds__(kThreads, 1)
                                           : ptx::smem_u32(&bars->tmem_empty[0]);
     // free slots below which a row is pruned between tiles (off the critical path)
     const int soft_slack = min(96, (CAP - a.k) / 2);
-    // lists longer than this are pruned while the warp would otherwise wait for its next
-    // accumulator tile (a select-prune keeps at most k + (CAP - k) / 4 keys, so this makes progress)
-    const int idle_min = a.idle_prune ? a.k + (CAP - a.k) / 4 + 32 : CAP;
     uint32_t tcount = 0;
     for_each_item(a, worker, n_workers, [&](const WorkItem& it) {
       const int64_t sp = it.sp;
@@ -427,15 +423,6 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int i = 0; i < (SAMPLE ? kSampleR : 1); ++i) top[i] = neg_inf;
       for (int64_t n0 = n_begin; n0 < n_end; n0 += BLOCK_N) {
         const uint32_t buf = tcount % kAccBufs, aphase = (tcount / kAccBufs) & 1u;
-        if (!SAMPLE && idle_min + 32 < CAP) {
-          // The epilogue warps are ahead of the MMA about a third of the time (ncu: 30 % of the
-          // samples sit in this wait), while a prune on the hand-over's critical path stalls the
-          // MMA issuer for all 16 warps of the pair.  So grown lists are pruned HERE, in the idle
-          // time, one row per poll; the thresholds tighten earlier as a by-product.
-          while (!__all_sync(kFull, ptx::mbar_try_wait(ptx::smem_u32(&bars->tmem_full[buf]), aphase))) {
-            if (!warp_maintain_one<ITEMS>(warp_lists, st, a.k, lane, idle_min)) break;
-          }
-        }
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[buf]), aphase, a.diag, 6);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BLOCK_N;
@@ -658,12 +645,6 @@ cudaError_t launch_t(const TcParams& p, int grid, cudaStream_t stream, float* du
   a.my_rank = p.my_rank;
   a.rows_per_owner = p.rows_per_owner;
   for (int g = 0; g < kMaxPeers; ++g) a.peer_out[g] = g < p.n_peers ? p.peer_out[g] : nullptr;
-  static int idle_prune = -1;
-  if (idle_prune < 0) {
-    const char* e = getenv("B200KNN_IDLE_PRUNE");
-    idle_prune = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  a.idle_prune = idle_prune;
   a.dump = dump;
   a.diag = diag;
   a.flags = flags;
