@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t tmem_empty_bar0 = PAIR ? ptx::mapa(ptx::smem_u32(&bars->tmem_empty[0]), 0)
                                           : ptx::smem_u32(&bars->tmem_empty[0]);
     // free slots below which a row is pruned between tiles (off the critical path)
-    const int soft_slack = min(96, (CAP - a.k) / 2);
+    const int soft_slack = min(40, (CAP - a.k) / 2);
     uint32_t tcount = 0;
     for_each_item(a, worker, n_workers, [&](const WorkItem& it) {
       const int64_t sp = it.sp;
