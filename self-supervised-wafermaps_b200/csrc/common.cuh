@@ -275,7 +275,12 @@ __device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, 
       if (kept >= 0) n_valid = kept;
       __syncwarp();
     }
-    if (n_valid <= 64) sort_store<2>(list, n_valid, k, lane, o);
+    // short lists (rows that ran under a good threshold in a small work item: the reference-shaped
+    // B = 64 call flushes ~146 of them per row) must not pay for a 64-key network each
+    if (n_valid == 0) {
+      for (int i = lane; i < k; i += 32) o[i] = 0ull;
+    } else if (n_valid <= 32) sort_store<1>(list, n_valid, k, lane, o);
+    else if (n_valid <= 64) sort_store<2>(list, n_valid, k, lane, o);
     else if (ITEMS >= 4 && n_valid <= 128) sort_store<(ITEMS >= 4 ? 4 : ITEMS)>(list, n_valid, k, lane, o);
     else if (ITEMS >= 8 && n_valid <= 256) sort_store<(ITEMS >= 8 ? 8 : ITEMS)>(list, n_valid, k, lane, o);
     else if (ITEMS >= 16 && n_valid <= 512) sort_store<(ITEMS >= 16 ? 16 : ITEMS)>(list, n_valid, k, lane, o);

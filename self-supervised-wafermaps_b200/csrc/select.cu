@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__
     if (kept >= 0) cnt = kept;
     __syncwarp();
   }
-  if (cnt <= 64) sort_store<2>(buf, cnt, k_out, lane, o);
+  if (cnt <= 32) sort_store<1>(buf, cnt, k_out, lane, o);
+  else if (cnt <= 64) sort_store<2>(buf, cnt, k_out, lane, o);
   else if (ITEMS >= 4 && cnt <= 128) sort_store<(ITEMS >= 4 ? 4 : ITEMS)>(buf, cnt, k_out, lane, o);
   else if (ITEMS >= 8 && cnt <= 256) sort_store<(ITEMS >= 8 ? 8 : ITEMS)>(buf, cnt, k_out, lane, o);
   else if (ITEMS >= 16 && cnt <= 512) sort_store<(ITEMS >= 16 ? 16 : ITEMS)>(buf, cnt, k_out, lane, o);
