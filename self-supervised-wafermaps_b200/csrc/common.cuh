@@ -259,9 +259,12 @@ __device__ __forceinline__ void sort_store(const uint64_t* list, int n, int k, i
 // long lists are first cut to ~k by radix-select.
 // `out_of(r)` returns where row r of the warp goes (a local buffer, or a peer GPU's exchange
 // buffer when the kernel scatters its results over NVLink).
+// unsorted_ok: the consumer is merge_kernel (bank splits, or the exchange buffer of a peer GPU),
+// which treats a list as a zero-terminated SET: rows that hold at most k keys are then copied as
+// they are — no sorting network on the item's tail, where the MMA pipe waits for the epilogue.
 template <int ITEMS, typename OutFn>
 __device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, int k, int lane,
-                                           unsigned valid_mask, OutFn out_of) {
+                                           unsigned valid_mask, OutFn out_of, bool unsorted_ok = false) {
   constexpr int CAP = ITEMS * 32;
   __syncwarp();
   for (int src = 0; src < 32; ++src) {
@@ -269,6 +272,10 @@ __device__ __forceinline__ void warp_flush(uint64_t* lists, const RowState& st, 
     int n_valid = __shfl_sync(kFull, int(st.cnt), src);
     uint64_t* list = lists + size_t(src) * CAP;
     uint64_t* o = out_of(src);
+    if (unsorted_ok && n_valid <= k) {
+      for (int i = lane; i < k; i += 32) o[i] = i < n_valid ? list[i] : 0ull;
+      continue;
+    }
     if (ITEMS > 8 && n_valid > 256 && n_valid > k) {
       int kept = -1;
       warp_prune_select<ITEMS>(list, n_valid, k, lane, &kept);

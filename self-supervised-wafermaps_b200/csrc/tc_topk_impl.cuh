@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                  (int64_t(a.my_rank) * a.rows_per_owner + (g - owner * a.rows_per_owner)) * a.k;
         }
         return a.out + (size_t(sp) * a.B + size_t(g)) * a.k;
-      });
+      }, a.n_peers > 0 || a.n_items > a.n_qtiles);  // exchange buffers and bank splits are merged afterwards
     });
   }
 
