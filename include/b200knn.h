@@ -267,7 +267,8 @@ size_t b200knn_rescore_workspace_bytes(int64_t B, int k_in);
  * b200knn_route_keys: out (n_shards, n, k): out[g][r][:] = the keys of row r whose bank row lies in
  *   [g*rows_per_shard, (g+1)*rows_per_shard), in their original order, compacted to the front and
  *   zero-padded — the send buffer of that exchange.  The shards re-score what they receive with
- *   b200knn_rescore (k_out = k_in; empty slots, and whole empty 32-slot units, are skipped).
+ *   b200knn_rescore (k_out = k_in).  Candidate lists are filled from the FRONT (empty slots only behind the last
+ *   candidate): the first empty 32-slot unit of a query ends it.
  * b200knn_certify: the certificate of b200knn_rescore on its own: exact_keys (B,k) merged exact
  *   keys, approx_keys (B,k_in) merged approximate candidates (both sorted descending);
  *   all_rows != 0 when k_in covers the whole bank.

@@ -805,7 +805,7 @@ def route_keys(keys: torch.Tensor, rows_per_shard: int, n_shards: int) -> torch.
 
 def rescore_sparse(feature: torch.Tensor, feature_bank: torch.Tensor, cand: torch.Tensor, cand_mode: str,
                    idx_offset: int) -> torch.Tensor:
-    """Exact (sequential-fma) keys of the candidates in `cand` (B, k_in; empty slots allowed anywhere;
+    """Exact (sequential-fma) keys of the candidates in `cand` (B, k_in; lists filled from the front, empty slots only behind the last candidate;
     indices offset by idx_offset into this bank), sorted descending, zero-padded: (B, k_in)."""
     lib = _lib.load()
     B, D = feature.shape

@@ -202,15 +202,19 @@ __global__ void __launch_bounds__(256)
     return (b < p.B && c < p.k_in) ? p.cand[b * p.k_in + c] : 0ull;
   };
 
-  // producer cursor: unit (pb, pg), chunk pc; this lane's key of that unit and of the next one
+  // producer cursor: unit (pb, pg), chunk pc; this lane's key of that unit, of the next unit of the
+  // same query and of the first unit of the next query (candidate lists are filled from the front:
+  // the first empty unit of a query ends it, and the cursor jumps to the next query)
   int64_t pu = u_begin, pb = u_begin / n_groups;
   int pg = int(u_begin - pb * n_groups), pc = 0, ps = 0;
   uint64_t p_key = load_key(pb, pg);
-  uint64_t p_key_next = (pu + 1 < u_end) ? (pg + 1 < n_groups ? load_key(pb, pg + 1) : load_key(pb + 1, 0)) : 0ull;
+  uint64_t p_key_next = pg + 1 < n_groups ? load_key(pb, pg + 1) : 0ull;
+  uint64_t p_key_nq = load_key(pb + 1, 0);
 
-  // One pipeline step = (unit, chunk).  A unit without candidates (routed lists of the sharded
-  // mode use ~1/G of their slots) takes ONE step — no copies, just the barrier handshake — and
-  // the consumer, which sees the same all-empty key words, advances in the same way.
+  // One pipeline step = (unit, chunk).  The first unit of a query without candidates (routed lists
+  // of the sharded mode use ~1/G of their slots) takes ONE step — no copies, just the barrier
+  // handshake — and ends the query: producer and consumer, which sees the same all-empty key
+  // words, both jump to the next query.
   auto produce = [&]() {
     Stage& st = stages[ps];
     const uint32_t bar = ptx::smem_u32(&bars[ps]);
@@ -241,20 +245,18 @@ __global__ void __launch_bounds__(256)
     if (++ps == STAGES) ps = 0;
     if (valid == 0u || ++pc == n_chunks) {
       pc = 0;
-      ++pu;
-      if (++pg == n_groups) {
-        pg = 0;
+      if (valid == 0u || pg + 1 == n_groups) {  // on to the next query
+        pu += n_groups - pg;
         ++pb;
+        pg = 0;
+        p_key = p_key_nq;
+        p_key_nq = load_key(pb + 1, 0);
+      } else {
+        ++pu;
+        ++pg;
+        p_key = p_key_next;
       }
-      p_key = p_key_next;
-      // prefetch the keys of the unit after the one now being produced
-      int64_t nb = pb;
-      int ng = pg + 1;
-      if (ng == n_groups) {
-        ng = 0;
-        ++nb;
-      }
-      p_key_next = (pu + 1 < u_end) ? load_key(nb, ng) : 0ull;
+      p_key_next = pg + 1 < n_groups ? load_key(pb, pg + 1) : 0ull;
     }
   };
 
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(256)
   int cs = 0, cc = 0;
   uint32_t phase = 0, klo = 0;
   int64_t cu = u_begin;
+  int cg = int(u_begin % n_groups);
   float acc = 0.0f;
   bool live = true;  // the unit holds at least one candidate
   while (cu < u_end) {
@@ -308,10 +311,15 @@ __global__ void __launch_bounds__(256)
         }
       }
     }
-    if (!live || ++cc == n_chunks) {
+    if (!live) {  // the rest of this query is empty (the select kernel masks by the candidate keys)
+      cc = 0;
+      cu += n_groups - cg;
+      cg = 0;
+    } else if (++cc == n_chunks) {
       cc = 0;
       tmp[cu * 32 + lane] = klo != 0 ? ((uint64_t(f32_to_orderable(acc)) << 32) | uint64_t(klo)) : 0ull;
       ++cu;
+      if (++cg == n_groups) cg = 0;
     }
     // the stage is free: order this warp's generic-proxy reads before the async-proxy refill
     __syncwarp();
@@ -359,8 +367,12 @@ __global__ void __launch_bounds__(128)
   int groups = 0;  // groups holding at least one key (candidate lists are filled from the front)
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
-    v[r] = r < n_groups ? mine[r * 32 + lane] : 0ull;
-    if (__any_sync(kFull, v[r] != 0ull)) groups = r + 1;
+    // a slot holds an exact key only where the candidate list holds a candidate (lists are filled
+    // from the front; the dot kernel does not touch the slots of empty units)
+    const int c = r * 32 + lane;
+    const bool has = r < n_groups && c < p.k_in && p.cand[b * p.k_in + c] != 0ull;
+    v[r] = has ? mine[c] : 0ull;
+    if (__any_sync(kFull, has)) groups = r + 1;
   }
   sort_groups<ITEMS>(v, groups, lane);
   if (p.n_peers > 0) {
