@@ -174,7 +174,7 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 }
 
 template <int CHUNK, int STAGES>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(384)
     rescore_dot_kernel(RescoreParams p, uint64_t* __restrict__ tmp, int n_groups, int64_t n_units,
                        int q_vec16) {
   using Stage = DotStage<CHUNK>;
@@ -494,12 +494,22 @@ cudaError_t launch_select_t(const RescoreParams& p, const uint64_t* tmp, int n_g
   return cudaGetLastError();
 }
 
-// experiment switch B200KNN_RESCORE_CHUNK=128|256 (columns per stage; default 128)
+// experiment switches B200KNN_RESCORE_CHUNK=64|128|256 (columns per stage) and B200KNN_RESCORE_STAGES=2|3|4
 int dot_chunk() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("B200KNN_RESCORE_CHUNK");
-    v = (e != nullptr && atoi(e) == 256) ? 256 : 128;
+    const int x = e != nullptr ? atoi(e) : 0;
+    v = (x == 256 || x == 64) ? x : 128;
+  }
+  return v;
+}
+int dot_stages() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("B200KNN_RESCORE_STAGES");
+    const int x = e != nullptr ? atoi(e) : 0;
+    v = (x == 3 || x == 4) ? x : 2;
   }
   return v;
 }
@@ -509,7 +519,7 @@ cudaError_t launch_dot_t(const RescoreParams& p, uint64_t* tmp, int n_groups, cu
   constexpr int kSmem = 232448 - 1024;
   const size_t per_warp = STAGES * (sizeof(DotStage<CHUNK>) + sizeof(uint64_t));
   int warps = int(kSmem / per_warp);
-  if (warps > 8) warps = 8;
+  if (warps > 12) warps = 12;
   if (warps < 1) return cudaErrorNotSupported;
   const int64_t n_units = p.B * n_groups;
   int64_t blocks = (n_units + warps - 1) / warps;
@@ -539,8 +549,14 @@ cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t works
   if (p.n_peers > 0 && !pipelined) return cudaErrorInvalidValue;  // the scatter lives in the pipelined variant
   if (pipelined) {
     uint64_t* tmp = static_cast<uint64_t*>(workspace);
-    cudaError_t e = dot_chunk() == 256 ? launch_dot_t<256, 2>(p, tmp, items, stream)
-                                       : launch_dot_t<128, 2>(p, tmp, items, stream);
+    cudaError_t e;
+    const int ch = dot_chunk(), stg = dot_stages();
+    if (ch == 256) e = launch_dot_t<256, 2>(p, tmp, items, stream);
+    else if (ch == 64 && stg == 2) e = launch_dot_t<64, 2>(p, tmp, items, stream);
+    else if (ch == 64 && stg == 3) e = launch_dot_t<64, 3>(p, tmp, items, stream);
+    else if (ch == 64) e = launch_dot_t<64, 4>(p, tmp, items, stream);
+    else if (stg == 3) e = launch_dot_t<128, 3>(p, tmp, items, stream);
+    else e = launch_dot_t<128, 2>(p, tmp, items, stream);
     if (e != cudaSuccess) return e;
     if (items <= 2) return launch_select_t<2>(p, tmp, items, stream);
     if (items <= 4) return launch_select_t<4>(p, tmp, items, stream);
