@@ -56,6 +56,10 @@ __device__ __forceinline__ int certified(const RescoreParams& p, uint64_t kth, u
   return (kth != 0) && (key_sim(kth) > key_sim(last) + e);
 }
 
+// slots per query in the workspace of the pipelined variant: k_in rounded up to 64 (work units of
+// up to 64 candidate slots)
+inline int ws_slots(int k_in) { return (k_in + 63) / 64 * 64; }
+
 constexpr int kWarps = 4;
 constexpr int kChunk = 64;            // d-columns staged per step
 constexpr int kTileLd = kChunk + 1;   // padded: lane c walks row c conflict-free
@@ -147,14 +151,18 @@ __global__ void __launch_bounds__(kWarps * 32)
 
 
 // ------------------------------------------------------------------ pipelined variant
-// One work unit = 32 consecutive candidate slots of one query; a step = one unit x one
-// CHUNK of columns.  Each warp owns STAGES stages and a contiguous range of units.
-template <int CHUNK>
+// One work unit = 32*R consecutive candidate slots of one query (lane l owns slots l, l+32, ...);
+// a step = one unit x one CHUNK of columns.  Each warp owns STAGES stages and a contiguous range
+// of units.  R = 2: every lane runs TWO independent fma chains, which is what hides the 4-cycle
+// dependent-fma latency with the 6 warps per SM the staging buffers leave room for — with one
+// chain per lane the kernel followed the SM clock (14.7 ms power-capped vs 10.0 ms at full clock
+// for the same 60 GB from HBM).
+template <int CHUNK, int R>
 struct DotStage {
   static constexpr int kPitch = CHUNK + 4;  // floats; lane c reads float4 j of row c: bank group (c + j) mod 8
-  float rows[32 * kPitch];
+  float rows[32 * R * kPitch];
   float q[CHUNK];
-  uint32_t klo[32];  // low key word (0xFFFFFFFF - idx) of each lane's candidate, 0 = empty slot
+  uint32_t klo[32 * R];  // low key word (0xFFFFFFFF - idx) of each candidate, 0 = empty slot
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -173,11 +181,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int CHUNK, int STAGES>
+// tmp: (B, n_groups * 32 * R) exact keys, slot c of query b at tmp[b * n_groups*32*R + c]
+template <int CHUNK, int STAGES, int R>
 __global__ void __launch_bounds__(384)
     rescore_dot_kernel(RescoreParams p, uint64_t* __restrict__ tmp, int n_groups, int64_t n_units,
                        int q_vec16) {
-  using Stage = DotStage<CHUNK>;
+  using Stage = DotStage<CHUNK, R>;
+  constexpr int kSlots = 32 * R;
   extern __shared__ __align__(16) unsigned char rs_smem[];
   const int n_warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,19 +207,27 @@ __global__ void __launch_bounds__(384)
   const int n_chunks = (p.dim_pad + CHUNK - 1) / CHUNK;
   const float* q32 = static_cast<const float*>(p.q);
 
-  auto load_key = [&](int64_t b, int g) -> uint64_t {
-    const int c = g * 32 + lane;
-    return (b < p.B && c < p.k_in) ? p.cand[b * p.k_in + c] : 0ull;
+  struct Keys {
+    uint64_t k[R];
+  };
+  auto load_keys = [&](int64_t b, int g) -> Keys {
+    Keys ks;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = g * kSlots + r * 32 + lane;
+      ks.k[r] = (b < p.B && g < n_groups && c < p.k_in) ? p.cand[b * p.k_in + c] : 0ull;
+    }
+    return ks;
   };
 
-  // producer cursor: unit (pb, pg), chunk pc; this lane's key of that unit, of the next unit of the
+  // producer cursor: unit (pb, pg), chunk pc; this lane's keys of that unit, of the next unit of the
   // same query and of the first unit of the next query (candidate lists are filled from the front:
   // the first empty unit of a query ends it, and the cursor jumps to the next query)
   int64_t pu = u_begin, pb = u_begin / n_groups;
   int pg = int(u_begin - pb * n_groups), pc = 0, ps = 0;
-  uint64_t p_key = load_key(pb, pg);
-  uint64_t p_key_next = pg + 1 < n_groups ? load_key(pb, pg + 1) : 0ull;
-  uint64_t p_key_nq = load_key(pb + 1, 0);
+  Keys p_key = load_keys(pb, pg);
+  Keys p_key_next = load_keys(pb, pg + 1);
+  Keys p_key_nq = load_keys(pb + 1, 0);
 
   // One pipeline step = (unit, chunk).  The first unit of a query without candidates (routed lists
   // of the sharded mode use ~1/G of their slots) takes ONE step — no copies, just the barrier
@@ -218,16 +236,23 @@ __global__ void __launch_bounds__(384)
   auto produce = [&]() {
     Stage& st = stages[ps];
     const uint32_t bar = ptx::smem_u32(&bars[ps]);
-    const int64_t row = p_key != 0 ? key_idx(p_key) - p.idx_offset : -1;
     const int d0 = pc * CHUNK;
     const int len = min(CHUNK, p.dim_pad - d0);
-    const unsigned valid = __ballot_sync(kFull, row >= 0);
-    if (lane == 0) ptx::mbar_expect_tx(bar, uint32_t(__popc(valid)) * uint32_t(len) * 4u);
-    if (row >= 0)
-      bulk_g2s(ptx::smem_u32(st.rows + lane * Stage::kPitch), p.rows_a + row * p.dim_pad + d0,
-               uint32_t(len) * 4u, bar);
+    int64_t row[R];
+    unsigned n_valid = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      row[r] = p_key.k[r] != 0 ? key_idx(p_key.k[r]) - p.idx_offset : -1;
+      n_valid += __popc(__ballot_sync(kFull, row[r] >= 0));
+    }
+    if (lane == 0) ptx::mbar_expect_tx(bar, n_valid * uint32_t(len) * 4u);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (row[r] >= 0)
+        bulk_g2s(ptx::smem_u32(st.rows + (r * 32 + lane) * Stage::kPitch), p.rows_a + row[r] * p.dim_pad + d0,
+                 uint32_t(len) * 4u, bar);
     const float* qrow = q32 + pb * p.q_ld;
-    if (valid == 0u) {
+    if (n_valid == 0u) {
     } else if (q_vec16) {
       for (int i = lane; i < len / 4; i += 32) {
         const int d = d0 + 4 * i;
@@ -241,73 +266,98 @@ __global__ void __launch_bounds__(384)
       }
     }
     cp_async_arrive_noinc(bar);
-    if (pc == 0) st.klo[lane] = row >= 0 ? uint32_t(p_key) : 0u;
+    if (pc == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) st.klo[r * 32 + lane] = row[r] >= 0 ? uint32_t(p_key.k[r]) : 0u;
+    }
     if (++ps == STAGES) ps = 0;
-    if (valid == 0u || ++pc == n_chunks) {
+    if (n_valid == 0u || ++pc == n_chunks) {
       pc = 0;
-      if (valid == 0u || pg + 1 == n_groups) {  // on to the next query
+      if (n_valid == 0u || pg + 1 == n_groups) {  // on to the next query
         pu += n_groups - pg;
         ++pb;
         pg = 0;
         p_key = p_key_nq;
-        p_key_nq = load_key(pb + 1, 0);
+        p_key_nq = load_keys(pb + 1, 0);
       } else {
         ++pu;
         ++pg;
         p_key = p_key_next;
       }
-      p_key_next = pg + 1 < n_groups ? load_key(pb, pg + 1) : 0ull;
+      p_key_next = load_keys(pb, pg + 1);
     }
   };
 
   for (int t = 0; t < STAGES && pu < u_end; ++t) produce();
 
   int cs = 0, cc = 0;
-  uint32_t phase = 0, klo = 0;
+  uint32_t phase = 0;
+  uint32_t klo[R];
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    klo[r] = 0u;
+    acc[r] = 0.0f;
+  }
   int64_t cu = u_begin;
   int cg = int(u_begin % n_groups);
-  float acc = 0.0f;
   bool live = true;  // the unit holds at least one candidate
   while (cu < u_end) {
     Stage& st = stages[cs];
     ptx::mbar_wait(ptx::smem_u32(&bars[cs]), phase, nullptr, 7);
     if (cc == 0) {
-      acc = 0.0f;
-      klo = st.klo[lane];
-      live = __any_sync(kFull, klo != 0u);
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r] = 0.0f;
+        klo[r] = st.klo[r * 32 + lane];
+        any = any || klo[r] != 0u;
+      }
+      live = __any_sync(kFull, any);
     }
     if (live) {
       const int len4 = min(CHUNK, p.dim_pad - cc * CHUNK) / 4;
-      const float4* xr = reinterpret_cast<const float4*>(st.rows + lane * Stage::kPitch);
       const float4* qr = reinterpret_cast<const float4*>(st.q);
-      // len4 is a multiple of 16 (dim_pad is a multiple of 64).  The 16 loads of a block are issued
-      // before its fma chain starts, and the next block's loads while the chain runs.
-      float4 x[8], w[8];
+      const float4* xr[R];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x[i] = xr[i];
+      for (int r = 0; r < R; ++r) xr[r] = reinterpret_cast<const float4*>(st.rows + (r * 32 + lane) * Stage::kPitch);
+      // len4 is a multiple of 16 (dim_pad is a multiple of 64).  The loads of a block of 4 float4 per
+      // row are issued before its fma chains start, and the next block's loads while they run; the
+      // R chains of a lane are independent and interleave in the pipeline.
+      constexpr int kBlk = 4;
+      float4 x[R][kBlk], w[kBlk];
+#pragma unroll
+      for (int i = 0; i < kBlk; ++i) {
         w[i] = qr[i];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r][i] = xr[r][i];
       }
 #pragma unroll 1
-      for (int j = 0; j < len4; j += 8) {
-        float4 xn[8], wn[8];
-        const int jn = (j + 8 < len4) ? j + 8 : j;
+      for (int j = 0; j < len4; j += kBlk) {
+        float4 xn[R][kBlk], wn[kBlk];
+        const int jn = (j + kBlk < len4) ? j + kBlk : j;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xn[i] = xr[jn + i];
+        for (int i = 0; i < kBlk; ++i) {
           wn[i] = qr[jn + i];
+#pragma unroll
+          for (int r = 0; r < R; ++r) xn[r][i] = xr[r][jn + i];
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc = __fmaf_rn(w[i].x, x[i].x, acc);
-          acc = __fmaf_rn(w[i].y, x[i].y, acc);
-          acc = __fmaf_rn(w[i].z, x[i].z, acc);
-          acc = __fmaf_rn(w[i].w, x[i].w, acc);
+        for (int i = 0; i < kBlk; ++i) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = __fmaf_rn(w[i].x, x[r][i].x, acc[r]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = __fmaf_rn(w[i].y, x[r][i].y, acc[r]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = __fmaf_rn(w[i].z, x[r][i].z, acc[r]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = __fmaf_rn(w[i].w, x[r][i].w, acc[r]);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          x[i] = xn[i];
+        for (int i = 0; i < kBlk; ++i) {
           w[i] = wn[i];
+#pragma unroll
+          for (int r = 0; r < R; ++r) x[r][i] = xn[r][i];
         }
       }
     }
@@ -317,7 +367,10 @@ __global__ void __launch_bounds__(384)
       cg = 0;
     } else if (++cc == n_chunks) {
       cc = 0;
-      tmp[cu * 32 + lane] = klo != 0 ? ((uint64_t(f32_to_orderable(acc)) << 32) | uint64_t(klo)) : 0ull;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        tmp[cu * kSlots + r * 32 + lane] =
+            klo[r] != 0 ? ((uint64_t(f32_to_orderable(acc[r])) << 32) | uint64_t(klo[r])) : 0ull;
       ++cu;
       if (++cg == n_groups) cg = 0;
     }
@@ -494,13 +547,12 @@ cudaError_t launch_select_t(const RescoreParams& p, const uint64_t* tmp, int n_g
   return cudaGetLastError();
 }
 
-// experiment switches B200KNN_RESCORE_CHUNK=64|128|256 (columns per stage) and B200KNN_RESCORE_STAGES=2|3|4
+// experiment switches B200KNN_RESCORE_CHUNK=64|128 (columns per stage; 64 = two chains per lane) and B200KNN_RESCORE_STAGES=2|3
 int dot_chunk() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("B200KNN_RESCORE_CHUNK");
-    const int x = e != nullptr ? atoi(e) : 0;
-    v = (x == 256 || x == 64) ? x : 128;
+    v = (e != nullptr && atoi(e) == 128) ? 128 : 64;
   }
   return v;
 }
@@ -509,23 +561,24 @@ int dot_stages() {
   if (v == 0) {
     const char* e = getenv("B200KNN_RESCORE_STAGES");
     const int x = e != nullptr ? atoi(e) : 0;
-    v = (x == 3 || x == 4) ? x : 2;
+    v = (x == 3) ? 3 : 2;
   }
   return v;
 }
 
-template <int CHUNK, int STAGES>
-cudaError_t launch_dot_t(const RescoreParams& p, uint64_t* tmp, int n_groups, cudaStream_t stream) {
+template <int CHUNK, int STAGES, int R>
+cudaError_t launch_dot_t(const RescoreParams& p, uint64_t* tmp, cudaStream_t stream) {
   constexpr int kSmem = 232448 - 1024;
-  const size_t per_warp = STAGES * (sizeof(DotStage<CHUNK>) + sizeof(uint64_t));
+  const size_t per_warp = STAGES * (sizeof(DotStage<CHUNK, R>) + sizeof(uint64_t));
   int warps = int(kSmem / per_warp);
   if (warps > 12) warps = 12;
   if (warps < 1) return cudaErrorNotSupported;
+  const int n_groups = ws_slots(p.k_in) / (32 * R);
   const int64_t n_units = p.B * n_groups;
   int64_t blocks = (n_units + warps - 1) / warps;
   if (blocks > 148) blocks = 148;
   const size_t smem = per_warp * warps;
-  auto kern = rescore_dot_kernel<CHUNK, STAGES>;
+  auto kern = rescore_dot_kernel<CHUNK, STAGES, R>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   const uintptr_t qa = reinterpret_cast<uintptr_t>(p.q);
@@ -535,9 +588,7 @@ cudaError_t launch_dot_t(const RescoreParams& p, uint64_t* tmp, int n_groups, cu
 }
 }  // namespace
 
-size_t rescore_workspace_bytes(int64_t B, int k_in) {
-  return size_t(B) * size_t((k_in + 31) / 32) * 32 * sizeof(uint64_t);
-}
+size_t rescore_workspace_bytes(int64_t B, int k_in) { return size_t(B) * size_t(ws_slots(k_in)) * sizeof(uint64_t); }
 
 cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t workspace_bytes,
                            cudaStream_t stream) {
@@ -551,18 +602,19 @@ cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t works
     uint64_t* tmp = static_cast<uint64_t*>(workspace);
     cudaError_t e;
     const int ch = dot_chunk(), stg = dot_stages();
-    if (ch == 256) e = launch_dot_t<256, 2>(p, tmp, items, stream);
-    else if (ch == 64 && stg == 2) e = launch_dot_t<64, 2>(p, tmp, items, stream);
-    else if (ch == 64 && stg == 3) e = launch_dot_t<64, 3>(p, tmp, items, stream);
-    else if (ch == 64) e = launch_dot_t<64, 4>(p, tmp, items, stream);
-    else if (stg == 3) e = launch_dot_t<128, 3>(p, tmp, items, stream);
-    else e = launch_dot_t<128, 2>(p, tmp, items, stream);
+    // default: 64 columns x 64 candidates per stage, two fma chains per lane (B200KNN_RESCORE_CHUNK=128: the
+    // one-chain variant with 128 columns x 32 candidates)
+    if (ch == 128 && stg == 2) e = launch_dot_t<128, 2, 1>(p, tmp, stream);
+    else if (ch == 128) e = launch_dot_t<128, 3, 1>(p, tmp, stream);
+    else if (stg == 3) e = launch_dot_t<64, 3, 2>(p, tmp, stream);
+    else e = launch_dot_t<64, 2, 2>(p, tmp, stream);
     if (e != cudaSuccess) return e;
-    if (items <= 2) return launch_select_t<2>(p, tmp, items, stream);
-    if (items <= 4) return launch_select_t<4>(p, tmp, items, stream);
-    if (items <= 8) return launch_select_t<8>(p, tmp, items, stream);
-    if (items <= 16) return launch_select_t<16>(p, tmp, items, stream);
-    if (items <= 32) return launch_select_t<32>(p, tmp, items, stream);
+    const int g32 = ws_slots(p.k_in) / 32;  // 32-slot groups per query in the workspace (always even)
+    if (g32 <= 2) return launch_select_t<2>(p, tmp, g32, stream);
+    if (g32 <= 4) return launch_select_t<4>(p, tmp, g32, stream);
+    if (g32 <= 8) return launch_select_t<8>(p, tmp, g32, stream);
+    if (g32 <= 16) return launch_select_t<16>(p, tmp, g32, stream);
+    if (g32 <= 32) return launch_select_t<32>(p, tmp, g32, stream);
     return cudaErrorInvalidValue;
   }
   if (items <= 2) return launch_rescore_t<2>(p, stream);
