@@ -153,10 +153,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 // ------------------------------------------------------------------ pipelined variant
 // One work unit = 32*R consecutive candidate slots of one query (lane l owns slots l, l+32, ...);
 // a step = one unit x one CHUNK of columns.  Each warp owns STAGES stages and a contiguous range
-// of units.  R = 2: every lane runs TWO independent fma chains, which is what hides the 4-cycle
-// dependent-fma latency with the 6 warps per SM the staging buffers leave room for — with one
-// chain per lane the kernel followed the SM clock (14.7 ms power-capped vs 10.0 ms at full clock
-// for the same 60 GB from HBM).
+// of units.  R = 2 (two independent fma chains per lane) is an experiment that did not pay, see
+// launch_rescore.
 template <int CHUNK, int R>
 struct DotStage {
   static constexpr int kPitch = CHUNK + 4;  // floats; lane c reads float4 j of row c: bank group (c + j) mod 8
@@ -556,6 +554,14 @@ int dot_chunk() {
   }
   return v;
 }
+int dot_rows() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("B200KNN_RESCORE_ROWS");
+    v = (e != nullptr && atoi(e) == 2) ? 2 : 1;
+  }
+  return v;
+}
 int dot_stages() {
   static int v = 0;
   if (v == 0) {
@@ -602,12 +608,16 @@ cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t works
     uint64_t* tmp = static_cast<uint64_t*>(workspace);
     cudaError_t e;
     const int ch = dot_chunk(), stg = dot_stages();
-    // default: 64 columns x 64 candidates per stage, two fma chains per lane (B200KNN_RESCORE_CHUNK=128: the
-    // one-chain variant with 128 columns x 32 candidates)
-    if (ch == 128 && stg == 2) e = launch_dot_t<128, 2, 1>(p, tmp, stream);
+    // default: 64 columns x 32 candidates per stage, 11 warps per SM.  Measured at the north-star step
+    // (74.5 GB of candidate rows, power-capped clocks): 128 columns / 6 warps 14.95 ms, 64 columns / 11 warps
+    // 13.96 ms, 3-4 stages with fewer warps 19.6-26.2 ms, two fma chains per lane over 64 candidates x 64
+    // columns (B200KNN_RESCORE_ROWS=2) 23.1 ms: the kernel is bound by the rate of its per-row bulk copies and
+    // by how many warps keep them in flight, not by the dependent-fma latency.
+    if (dot_rows() == 2) e = launch_dot_t<64, 2, 2>(p, tmp, stream);
+    else if (ch == 128 && stg == 2) e = launch_dot_t<128, 2, 1>(p, tmp, stream);
     else if (ch == 128) e = launch_dot_t<128, 3, 1>(p, tmp, stream);
-    else if (stg == 3) e = launch_dot_t<64, 3, 2>(p, tmp, stream);
-    else e = launch_dot_t<64, 2, 2>(p, tmp, stream);
+    else if (stg == 3) e = launch_dot_t<64, 3, 1>(p, tmp, stream);
+    else e = launch_dot_t<64, 2, 1>(p, tmp, stream);
     if (e != cudaSuccess) return e;
     const int g32 = ws_slots(p.k_in) / 32;  // 32-slot groups per query in the workspace (always even)
     if (g32 <= 2) return launch_select_t<2>(p, tmp, g32, stream);
