@@ -22,11 +22,10 @@ namespace {
 // first warp then folds the other buffers into its own; the list fetches of a row are then
 // wpr-way parallel instead of one dependent chain (45 us -> ~10 us for 64 rows x 74 lists).
 template <int ITEMS>
-__global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__ in, int G,
-                                                    int64_t B, int k_in, int k_out,
-                                                    uint64_t* __restrict__ out, int wpr) {
+__device__ __forceinline__ void merge_rows_body(const uint64_t* __restrict__ in, int G, int64_t B, int k_in,
+                                                int k_out, uint64_t* __restrict__ out, int wpr,
+                                                uint64_t* merge_smem) {
   constexpr int CAP = ITEMS * 32;
-  extern __shared__ __align__(16) uint64_t merge_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int n_warps = blockDim.x >> 5;
@@ -123,6 +122,147 @@ __global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__
   else sort_store<ITEMS>(buf, cnt, k_out, lane, o);
 }
 
+template <int ITEMS>
+__global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__ in, int G,
+                                                    int64_t B, int k_in, int k_out,
+                                                    uint64_t* __restrict__ out, int wpr) {
+  extern __shared__ __align__(16) uint64_t merge_smem[];
+  merge_rows_body<ITEMS>(in, G, B, k_in, k_out, out, wpr, merge_smem);
+}
+
+// Few rows, many lists (the reference-shaped B = 64 call: one list per bank split and row, ~138 of
+// them, mostly short because every split ran under the sampled threshold).  One 8-warp block per
+// row: (1) all warps gather the non-empty keys of the row's lists into shared memory (slots from
+// one atomic counter); (2) if more than the sorting network holds survive, a block-wide radix
+// select on the 64-bit keys finds a threshold that keeps between k_out and CAP of them (early
+// exit, a handful of counting rounds); (3) one warp sorts the survivors once.  The warp-serial
+// variant above spends its time folding eight partial buffers through one warp (60 us for 64 rows
+// x 138 lists at k = 240; this one: one gather, ~3 counting rounds, one sort).  Rows whose lists
+// do not fit the staging buffer (no threshold: every split returns k_in keys) or whose keys tie
+// beyond the network take the warp-serial path inside the same block.
+constexpr int kStage = 4096;  // keys staged per row
+template <int ITEMS>
+__global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __restrict__ in, int G, int64_t B,
+                                                          int k_in, int k_out, uint64_t* __restrict__ out) {
+  constexpr int CAP = ITEMS * 32;
+  constexpr int kPerThread = kStage / 256;
+  extern __shared__ __align__(16) uint64_t merge_smem[];
+  __shared__ int s_n, s_over, s_red[8];
+  __shared__ unsigned long long s_and[8], s_or[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row = blockIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  if (tid == 0) {
+    s_n = 0;
+    s_over = 0;
+  }
+  __syncthreads();
+  // (1) gather
+  for (int g = warp; g < G; g += 8) {
+    const uint64_t* list = in + (int64_t(g) * B + row) * k_in;
+    for (int j0 = 0; j0 < k_in; j0 += 32) {
+      const uint64_t key = j0 + lane < k_in ? list[j0 + lane] : 0ull;
+      const unsigned bm = __ballot_sync(kFull, key != 0ull);
+      if (bm == 0u) break;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, __popc(bm));
+      base = __shfl_sync(kFull, base, 0);
+      if (base + __popc(bm) <= kStage) {
+        if (key != 0ull) merge_smem[base + __popc(bm & lt_mask)] = key;
+      } else if (lane == 0) {
+        s_over = 1;
+      }
+      if (bm != kFull) break;
+    }
+  }
+  __syncthreads();
+  int n = s_n;
+  bool slow = s_over != 0;
+  uint64_t* o = out + row * k_out;
+  if (!slow && n > CAP) {
+    // (2) block-wide radix select: threshold T with k_out <= #{key >= T} <= CAP
+    uint64_t v[kPerThread];
+    uint64_t a = ~0ull, r = 0ull;
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      const int idx = i * 256 + tid;
+      v[i] = idx < n ? merge_smem[idx] : 0ull;
+      if (idx < n) {
+        a &= v[i];
+        r |= v[i];
+      }
+    }
+    a = (uint64_t(__reduce_and_sync(kFull, uint32_t(a >> 32))) << 32) | __reduce_and_sync(kFull, uint32_t(a));
+    r = (uint64_t(__reduce_or_sync(kFull, uint32_t(r >> 32))) << 32) | __reduce_or_sync(kFull, uint32_t(r));
+    if (lane == 0) {
+      s_and[warp] = a;
+      s_or[warp] = r;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a &= s_and[w];
+      r |= s_or[w];
+    }
+    uint64_t T = a, open_bits = a ^ r;
+    int c = n;
+    while (open_bits) {
+      const uint64_t bit = 1ull << (63 - __clzll(open_bits));
+      open_bits &= ~bit;
+      const uint64_t cand = T | bit;
+      int cc = 0;
+#pragma unroll
+      for (int i = 0; i < kPerThread; ++i) cc += (v[i] >= cand) ? 1 : 0;
+      cc = __reduce_add_sync(kFull, cc);
+      __syncthreads();  // previous round's s_red reads are done
+      if (lane == 0) s_red[warp] = cc;
+      __syncthreads();
+      cc = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) cc += s_red[w];
+      if (cc >= k_out) {
+        T = cand;
+        c = cc;
+        if (c <= CAP) break;
+      }
+    }
+    if (c > CAP) {
+      slow = true;  // ties beyond the network (identical keys of the sampling variant): sort-based path
+    } else {
+      // compact the survivors to the front of the staging buffer (every key is in registers by now)
+      __syncthreads();
+      if (tid == 0) s_n = 0;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kPerThread; ++i) {
+        const bool keep = v[i] >= T && v[i] != 0ull;
+        const unsigned bm = __ballot_sync(kFull, keep);
+        int base = 0;
+        if (lane == 0 && bm != 0u) base = atomicAdd(&s_n, __popc(bm));
+        base = __shfl_sync(kFull, base, 0);
+        if (keep) merge_smem[base + __popc(bm & lt_mask)] = v[i];
+      }
+      __syncthreads();
+      n = s_n;
+    }
+  }
+  if (slow) {  // uniform over the block
+    __syncthreads();
+    merge_rows_body<ITEMS>(in, G, B, k_in, k_out, out, 8, merge_smem);
+    return;
+  }
+  // (3) one sort of what is left (n <= CAP)
+  if (warp != 0) return;
+  if (n == 0) {
+    for (int i = lane; i < k_out; i += 32) o[i] = 0ull;
+  } else if (n <= 32) sort_store<1>(merge_smem, n, k_out, lane, o);
+  else if (n <= 64) sort_store<2>(merge_smem, n, k_out, lane, o);
+  else if (ITEMS >= 4 && n <= 128) sort_store<(ITEMS >= 4 ? 4 : ITEMS)>(merge_smem, n, k_out, lane, o);
+  else if (ITEMS >= 8 && n <= 256) sort_store<(ITEMS >= 8 ? 8 : ITEMS)>(merge_smem, n, k_out, lane, o);
+  else if (ITEMS >= 16 && n <= 512) sort_store<(ITEMS >= 16 ? 16 : ITEMS)>(merge_smem, n, k_out, lane, o);
+  else sort_store<ITEMS>(merge_smem, n, k_out, lane, o);
+}
+
 __global__ void decode_kernel(const uint64_t* __restrict__ keys, int64_t n, float* __restrict__ sims,
                               int64_t* __restrict__ idx) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -143,11 +283,18 @@ cudaError_t launch_merge_t(const uint64_t* in, int G, int64_t B, int k_in, int k
                            cudaStream_t stream) {
   // few rows: one row per CTA so that the rows spread over the SMs, and — when there are many
   // lists — several warps per row
-  int warps = 4, wpr = 1;
-  if (B < 148 * 8) {
-    wpr = G >= 16 ? 8 : (G >= 8 ? 4 : 1);
-    warps = wpr;
+  if (B < 148 * 8 && G >= 8) {  // few rows, many lists: one block per row, block-wide select
+    const size_t stage = size_t(kStage) > size_t(8) * ITEMS * 32 ? size_t(kStage) : size_t(8) * ITEMS * 32;
+    const size_t smem = stage * sizeof(uint64_t) + sizeof(int) * 8;
+    auto kern = merge_small_kernel<ITEMS>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<unsigned(B), 256, smem, stream>>>(in, G, B, k_in, k_out, out);
+    return cudaGetLastError();
   }
+  int warps = 4, wpr = 1;
   const int64_t blocks = (B + warps / wpr - 1) / (warps / wpr);
   const size_t smem = size_t(warps) * ITEMS * 32 * sizeof(uint64_t) + sizeof(int) * warps;
   auto kern = merge_kernel<ITEMS>;
