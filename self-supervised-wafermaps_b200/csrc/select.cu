@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__
 // beyond the network take the warp-serial path inside the same block.
 constexpr int kStage = 4096;  // keys staged per row
 template <int ITEMS>
-__global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __restrict__ in, int G, int64_t B,
+__global__ void __launch_bounds__(256, 2) merge_small_kernel(const uint64_t* __restrict__ in, int G, int64_t B,
                                                           int k_in, int k_out, uint64_t* __restrict__ out) {
   constexpr int CAP = ITEMS * 32;
   constexpr int kPerThread = kStage / 256;
@@ -157,22 +157,38 @@ __global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __rest
     s_over = 0;
   }
   __syncthreads();
-  // (1) gather
-  for (int g = warp; g < G; g += 8) {
+  // (1) gather: one THREAD per list (the lists are short and sit at unrelated addresses, so the
+  // parallelism that hides the load latency is across lists, 256 at a time); a list longer than
+  // kLong keys means it ran without a useful threshold, and the row takes the warp-serial path
+  constexpr int kLong = 64;
+  const bool pairs = (k_in % 2) == 0;  // 16-byte loads of two keys (list bases are then 16-byte aligned)
+  for (int g = tid; g < G; g += 256) {
     const uint64_t* list = in + (int64_t(g) * B + row) * k_in;
-    for (int j0 = 0; j0 < k_in; j0 += 32) {
-      const uint64_t key = j0 + lane < k_in ? list[j0 + lane] : 0ull;
-      const unsigned bm = __ballot_sync(kFull, key != 0ull);
-      if (bm == 0u) break;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_n, __popc(bm));
-      base = __shfl_sync(kFull, base, 0);
-      if (base + __popc(bm) <= kStage) {
-        if (key != 0ull) merge_smem[base + __popc(bm & lt_mask)] = key;
-      } else if (lane == 0) {
-        s_over = 1;
+    for (int j = 0; j < k_in;) {
+      uint64_t k0, k1 = 0ull;
+      if (pairs) {
+        const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(list + j);
+        k0 = kk.x;
+        k1 = kk.y;
+      } else {
+        k0 = list[j];
       }
-      if (bm != kFull) break;
+      const int c = (k0 != 0ull ? 1 : 0) + ((k0 != 0ull && k1 != 0ull) ? 1 : 0);
+      if (c == 0) break;
+      if (j + c > kLong) {
+        s_over = 1;
+        break;
+      }
+      const int base = atomicAdd(&s_n, c);
+      if (base + c <= kStage) {
+        merge_smem[base] = k0;
+        if (c == 2) merge_smem[base + 1] = k1;
+      } else {
+        s_over = 1;
+        break;
+      }
+      if (c < (pairs ? 2 : 1)) break;
+      j += pairs ? 2 : 1;
     }
   }
   __syncthreads();
