@@ -613,8 +613,10 @@ cudaError_t launch_rescore(const RescoreParams& p, void* workspace, size_t works
     // 13.96 ms, 3-4 stages with fewer warps 19.6-26.2 ms, two fma chains per lane over 64 candidates x 64
     // columns (B200KNN_RESCORE_ROWS=2) 23.1 ms: the kernel is bound by the rate of its per-row bulk copies and
     // by how many warps keep them in flight, not by the dependent-fma latency.
+    // small calls (the reference-shaped B = 64) are latency-bound chains of steps: fewer, larger steps
+    const bool small_call = p.B * int64_t(ws_slots(p.k_in) / 32) < 148 * 12 * 8;
     if (dot_rows() == 2) e = launch_dot_t<64, 2, 2>(p, tmp, stream);
-    else if (ch == 128 && stg == 2) e = launch_dot_t<128, 2, 1>(p, tmp, stream);
+    else if ((ch == 128 || small_call) && stg == 2) e = launch_dot_t<128, 2, 1>(p, tmp, stream);
     else if (ch == 128) e = launch_dot_t<128, 3, 1>(p, tmp, stream);
     else if (stg == 3) e = launch_dot_t<64, 3, 1>(p, tmp, stream);
     else e = launch_dot_t<64, 2, 1>(p, tmp, stream);
