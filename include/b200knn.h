@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200KNN_VERSION 141 /* 0.1.4.1: + b200knn_plan_info_ex; 0.1.4: + b200knn_topk_exact_below (k > 992), b200knn_route_scatter, b200knn_rescore_scatter,
+#define B200KNN_VERSION 142 /* 0.1.4.2: + b200knn_topk_sample_scatter, b200knn_broadcast_f32; 0.1.4.1: + b200knn_plan_info_ex; 0.1.4: + b200knn_topk_exact_below (k > 992), b200knn_route_scatter, b200knn_rescore_scatter,
                               b200knn_compact_rows, b200knn_scatter_rows (sync-free sharded fp32 mode); 0.1.3: + B200KNN_MODE_F16; 0.1.2: + b200knn_route_keys, b200knn_certify (sharded fp32 mode); 0.1.1: b200knn_rescore workspace */
 
 /* error codes */
@@ -296,6 +296,17 @@ int b200knn_certify(const void* q, int q_dtype, int64_t q_ld, int dim, const uin
  *   runs on a fixed-capacity sub-batch without a host read.
  * b200knn_scatter_rows: dst[rows[i]*dst_ld + c] = src[i*src_ld + c], c < width, i < min(n, *count).
  */
+/* The sharded threshold exchange over peer memory: b200knn_topk_sample whose 16 values of query row b go into
+ * the exchange buffer of the GPU that owns b (host_peer_out[b / rows_per_owner] + ((my_rank * rows_per_owner +
+ * b % rows_per_owner) * 16); refused (B200KNN_E_UNSUPPORTED) when the sample is planned with bank splits), and
+ * b200knn_broadcast_f32: dst[g][dst_offset + i] = src[i] for every peer g (the owner publishes its thresholds). */
+int b200knn_topk_sample_scatter(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
+                                const void* bank_lo, int64_t B, int64_t n_visit, int dim,
+                                int64_t bank_row_stride, const void* const* host_peer_out, int n_peers,
+                                int my_rank, int64_t rows_per_owner, void* workspace, size_t workspace_bytes,
+                                void* stream);
+int b200knn_broadcast_f32(const float* src, int64_t n, const void* const* host_peer_dst, int n_peers,
+                          int64_t dst_offset, void* stream);
 int b200knn_route_scatter(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int n_shards,
                           const void* const* host_inbox, int64_t row_offset, void* stream);
 int b200knn_rescore_scatter(const float* q, int64_t q_ld, const float* rows, int64_t N, int dim,

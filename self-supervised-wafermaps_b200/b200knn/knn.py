@@ -572,6 +572,52 @@ def sample_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode:
                         sample=(r == _lib.SAMPLE_R and PREPASS["register_sample"]))
 
 
+def sample_scatter_supported(B: int, n_rows: int, D: int, k: int, mode: str, n_rows_for_decision: int) -> bool:
+    """Whether sample_scatter applies to a shard of n_rows rows (pre-pass on, sample planned without splits)."""
+    s = prepass_stride(n_rows_for_decision, k, B)
+    if s == 0 or mode not in TC_MODES or PREPASS["r"] != _lib.SAMPLE_R or not PREPASS["register_sample"]:
+        return False
+    n_visit = (n_rows + s - 1) // s
+    if n_visit < PREPASS["r"]:
+        return False
+    try:
+        return plan_info(B, n_visit, D, PREPASS["r"], effective_mode(mode, D))["splits"] == 1
+    except RuntimeError:
+        return False
+
+
+def sample_scatter(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: str, n_rows_for_decision: int,
+                   peer_ptrs, rank: int, rows_per_owner: int) -> None:
+    """sample_keys whose (B, 16) sample of query row b is stored straight into the exchange buffer of
+    the GPU that owns b (the sharded threshold exchange over NVLink peer memory)."""
+    lib = _lib.load()
+    N = feature_bank.shape[1]
+    B, D = feature.shape
+    s = prepass_stride(n_rows_for_decision, k, B)
+    mode = effective_mode(mode, D)
+    n_visit = (N + s - 1) // s
+    dev = feature.device
+    with torch.cuda.device(dev):
+        pb = bank_cache.get(feature_bank, mode)
+        pq = query_cache.get(feature, mode)
+        ws_bytes = lib.b200knn_topk_workspace_bytes(B, n_visit, D, PREPASS["r"], _lib.MODES[mode])
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200knn_topk_sample_scatter(_lib.MODES[mode], pq.hi.data_ptr(), _ptr(pq.lo), pb.hi.data_ptr(),
+                                                   _ptr(pb.lo), B, n_visit, D, s, _ptr_array(peer_ptrs), len(peer_ptrs),
+                                                   rank, rows_per_owner, ws.data_ptr(), ws_bytes, _stream()),
+                   "topk_sample_scatter")
+
+
+def broadcast_f32(src: torch.Tensor, peer_ptrs, dst_offset: int) -> None:
+    """dst[g][dst_offset + i] = src[i] on every peer g (device pointers of every rank's fp32 buffer)."""
+    src = src.contiguous()
+    assert src.dtype == torch.float32
+    if src.numel():
+        with torch.cuda.device(src.device):
+            _lib.check(_lib.load().b200knn_broadcast_f32(src.data_ptr(), src.numel(), _ptr_array(peer_ptrs),
+                                                         len(peer_ptrs), dst_offset, _stream()), "broadcast_f32")
+
+
 def topk_keys(feature: torch.Tensor, feature_bank: torch.Tensor, k: int, mode: Optional[str] = None,
               idx_offset: int = 0, tau0: Optional[torch.Tensor] = None, repair: bool = True,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -253,6 +253,38 @@ int b200knn_topk_sample(int mode, const void* q_hi, const void* q_lo, const void
                    nullptr, true);
 }
 
+int b200knn_topk_sample_scatter(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
+                                const void* bank_lo, int64_t B, int64_t n_visit, int dim,
+                                int64_t bank_row_stride, const void* const* host_peer_out, int n_peers,
+                                int my_rank, int64_t rows_per_owner, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (!is_tc_mode(mode)) return fail(B200KNN_E_ARG, "topk_sample_scatter: tensor-core modes only");
+  if (bank_row_stride < 1) return fail(B200KNN_E_ARG, "topk_sample_scatter: bank_row_stride must be >= 1");
+  if (n_visit < B200KNN_SAMPLE_R) return fail(B200KNN_E_ARG, "topk_sample_scatter: fewer than 16 rows to sample");
+  if (!host_peer_out || n_peers < 1 || n_peers > 8 || my_rank < 0 || my_rank >= n_peers)
+    return fail(B200KNN_E_ARG, "topk_sample_scatter: 1..8 peers and a rank among them");
+  if (rows_per_owner <= 0 || rows_per_owner * n_peers < B)
+    return fail(B200KNN_E_ARG, "topk_sample_scatter: rows_per_owner * n_peers must cover B");
+  for (int g = 0; g < n_peers; ++g)
+    if (!host_peer_out[g]) return fail(B200KNN_E_ARG, "topk_sample_scatter: null peer buffer");
+  return topk_impl(mode, q_hi, q_lo, 0, 0, bank_hi, bank_lo, 0, 0, 0, B, n_visit, dim, B200KNN_SAMPLE_R, 0, nullptr,
+                   workspace, workspace_bytes, stream, nullptr, nullptr, 0, bank_row_stride, nullptr, true,
+                   host_peer_out, n_peers, my_rank, rows_per_owner);
+}
+
+int b200knn_broadcast_f32(const float* src, int64_t n, const void* const* host_peer_dst, int n_peers,
+                          int64_t dst_offset, void* stream) {
+  if (!src || !host_peer_dst || n < 0 || n_peers < 1 || n_peers > 8 || dst_offset < 0)
+    return fail(B200KNN_E_ARG, "broadcast_f32: bad argument (1..8 peers)");
+  float* dst[8];
+  for (int g = 0; g < n_peers; ++g) {
+    if (!host_peer_dst[g]) return fail(B200KNN_E_ARG, "broadcast_f32: null peer buffer");
+    dst[g] = static_cast<float*>(const_cast<void*>(host_peer_dst[g]));
+  }
+  cudaError_t e = b200knn::launch_broadcast_f32(src, n, dst, n_peers, dst_offset, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200KNN_OK : fail_cuda("broadcast_f32", e);
+}
+
 int b200knn_topk_scatter(int mode, const void* q_hi, const void* q_lo, const void* bank_hi,
                          const void* bank_lo, int64_t B, int64_t N, int dim, int k, int64_t idx_offset,
                          const float* tau0, const void* const* host_peer_out, int n_peers, int my_rank,

@@ -88,6 +88,8 @@ cudaError_t launch_route_keys(const uint64_t* keys, int64_t n, int k, int64_t ro
 // sharded_ops.cu
 cudaError_t launch_route_scatter(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int G,
                                  uint64_t* const* inbox, int64_t row_offset, cudaStream_t stream);
+cudaError_t launch_broadcast_f32(const float* src, int64_t n, float* const* dst, int G, int64_t dst_offset,
+                                 cudaStream_t stream);
 cudaError_t launch_compact_rows(const int64_t* status, int64_t ld, int64_t n, int64_t mask, int64_t* rows_out,
                                 int cap, int32_t* count_out, cudaStream_t stream);
 cudaError_t launch_scatter_rows(int64_t* dst, int64_t dst_ld, const int64_t* src, int64_t src_ld,

@@ -96,7 +96,31 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// dst[g][dst_offset + i] = src[i] for every peer g: the query owner publishes its rows' thresholds
+struct PeerF32 {
+  float* p[kMaxPeers];
+};
+__global__ void __launch_bounds__(256)
+    broadcast_f32_kernel(const float* __restrict__ src, int64_t n, PeerF32 dst, int G, int64_t dst_offset) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+#pragma unroll
+  for (int g = 0; g < kMaxPeers; ++g)
+    if (g < G) dst.p[g][dst_offset + i] = v;
+}
+
 }  // namespace
+
+cudaError_t launch_broadcast_f32(const float* src, int64_t n, float* const* dst, int G, int64_t dst_offset,
+                                 cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  if (G < 1 || G > kMaxPeers) return cudaErrorInvalidValue;
+  PeerF32 pp;
+  for (int g = 0; g < kMaxPeers; ++g) pp.p[g] = g < G ? dst[g] : nullptr;
+  broadcast_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(src, n, pp, G, dst_offset);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_route_scatter(const uint64_t* keys, int64_t n, int k, int64_t rows_per_shard, int G,
                                  uint64_t* const* inbox, int64_t row_offset, cudaStream_t stream) {

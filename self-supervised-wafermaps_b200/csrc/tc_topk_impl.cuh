@@ -532,7 +532,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if (SAMPLE) {
         if (owner && grow < a.B) {
-          uint64_t* o = a.out + (size_t(sp) * a.B + grow) * kSampleR;
+          uint64_t* o;
+          if (a.n_peers > 0) {  // sharded threshold exchange: straight into the query owner's buffer
+            const int64_t own = grow / a.rows_per_owner;
+            o = a.peer_out[own] + (int64_t(a.my_rank) * a.rows_per_owner + (grow - own * a.rows_per_owner)) * kSampleR;
+          } else {
+            o = a.out + (size_t(sp) * a.B + grow) * kSampleR;
+          }
 #pragma unroll
           for (int i = 0; i < kSampleR; ++i) o[i] = top[i] > neg_inf ? make_key(top[i], 0u) : 0ull;
         }

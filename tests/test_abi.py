@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.b200knn_version() == 141
+    assert lib.b200knn_version() == 142
     assert isinstance(lib.b200knn_last_error(), bytes)
 
 
