@@ -253,12 +253,20 @@ class ShardedBank:
         dist.all_gather_into_tensor(tau, tau_own.contiguous(), group=self.group)
         return tau[:B].contiguous()
 
+    # OFF by default (B200KNN_FUSED_THRESHOLD=1 switches it on).  Measured at 8 GPUs
+    # (profiles/r02_call25_* vs r02_call23_*): the resident step is unchanged (16.99 vs 16.78 ms fp32 — what
+    # the phase log shows at a step's first synchronisation point is the ranks' arrival skew, whichever
+    # primitive implements it), but the end-to-end step with the concurrent NCCL all-gather of the next
+    # batch on the copy stream got 24-30 % slower, so the NCCL exchange stays the default.
+    fused_threshold = os.environ.get("B200KNN_FUSED_THRESHOLD", "0") == "1"
+
     def _global_threshold_fused(self, feature: torch.Tensor, k: int) -> Optional[torch.Tensor]:
-        """global_threshold over NVLink peer memory (the NCCL all-to-all of the (B,16) samples cost
-        1.4-2.3 ms per call at 4-8 GPUs): the sampling kernel stores every query's 16 values into the
-        query owner's buffer, the owner merges the G samples of its rows and stores their thresholds
-        into every rank's threshold buffer; three symmetric-memory barriers, no NCCL call."""
-        if not (self.fused_exchange and feature.is_cuda and hasattr(self.ops, "sample_scatter")):
+        """global_threshold over NVLink peer memory: the sampling kernel stores every query's 16
+        values into the query owner's buffer, the owner merges the G samples of its rows and stores
+        their thresholds into every rank's threshold buffer; three symmetric-memory barriers, no
+        NCCL call."""
+        if not (self.fused_threshold and self.fused_exchange and feature.is_cuda
+                and hasattr(self.ops, "sample_scatter")):
             return None
         G = self.world_size
         B, D = feature.shape

@@ -47,7 +47,10 @@ def run_cases(rank, dev, log=None):
             p4 = sb.knn_predict(q, C, k, 0.1)
             b200knn.ShardedBank.fused_exchange = True
             p5 = sb.knn_predict(q, C, k, 0.1)                        # buffers reused across calls
-            ok = bool(torch.equal(single, sharded)) and all(bool(torch.equal(p1, p)) for p in (p2, p3, p4, p5))
+            b200knn.ShardedBank.fused_threshold = True                 # threshold exchange over peer memory too
+            p6 = sb.knn_predict(q, C, k, 0.1)
+            b200knn.ShardedBank.fused_threshold = False
+            ok = bool(torch.equal(single, sharded)) and all(bool(torch.equal(p1, p)) for p in (p2, p3, p4, p5, p6))
             if log is not None:
                 log(f"rank {rank} N={N} D={D} B={B} k={k} {kind} mode={mode}: sharded==single {ok}")
             if not ok:
