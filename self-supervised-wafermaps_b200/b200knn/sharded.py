@@ -542,10 +542,10 @@ class ShardedBank:
         Level 1 (all rows): `_owned_keys_rescored` at the cascade's first level.  Rows it leaves
         uncertified or starved (status bits 3 / 0 — identical on every rank after the all-gather)
         are compacted ON THE DEVICE into a fixed-capacity sub-batch; level 2 recomputes that
-        sub-batch exactly on every shard's own rows (single-GPU cascade level 2: fp16 x split-fp16
-        candidates + exact re-scoring + the shard-local certificate — a shard holds 1/G of the bank,
-        so its rank gaps are G times wider), the per-shard exact top-k are all-gathered and merged
-        and the rankings scattered back.  Only then is one status word read; rows still open (level 2
+        sub-batch exactly on every shard's own rows (one cascade level at base margin — fp16 again
+        with 4 or more shards, fp16 x split-fp16 below that — + exact re-scoring + the shard-local
+        certificate: a shard holds 1/G of the bank, so its rank gaps are G times wider), the per-shard
+        exact top-k are all-gathered and merged and the rankings scattered back.  Only then is one status word read; rows still open (level 2
         uncertified on some shard, or more open rows than the capacity) take the host-driven path."""
         B = feature.shape[0]
         self._mark("start")
