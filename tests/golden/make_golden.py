@@ -8,6 +8,7 @@ lightly is not installable here, so these pin the restatement, not lightly):
                      data/interim/model_preds/<model>_preds_subset.pkl.xz
                      (12,449 x 512 fp16 + failureCode), plus R32 / O64 / SEQ outputs
   synth.npz          R32 / O64 / SEQ outputs of the seeded cases in tests/datagen.py
+  synth_nonneg.npz   the same for the non-negative cases (datagen.RELU_CASE_NAMES, round 2)
 """
 import os
 import sys
@@ -85,7 +86,21 @@ def synth():
     print("synth", len(res))
 
 
+def synth_nonneg():
+    """Round 2: non-negative (post-ReLU-like) embeddings, the reference's real input distribution."""
+    res = {}
+    for name in datagen.RELU_CASE_NAMES:
+        c = datagen.make_case(name)
+        res.update(outputs(c["feature"], c["bank"], c["labels"], c["C"], c["k"], c["t"], name + "_"))
+    np.savez_compressed(os.path.join(HERE, "synth_nonneg.npz"), **res)
+    print("synth_nonneg", len(res))
+
+
 if __name__ == "__main__":
+    if "--nonneg-only" in sys.argv:
+        synth_nonneg()
+        sys.exit(0)
     synth()
+    synth_nonneg()
     for m in ("FastSiam", "SimSiam"):
         real(m)

@@ -21,10 +21,12 @@ def _t(x):
 
 @pytest.fixture(scope="module")
 def synth(golden_dir):
-    return np.load(os.path.join(golden_dir, "synth.npz"))
+    both = dict(np.load(os.path.join(golden_dir, "synth.npz")))
+    both.update(np.load(os.path.join(golden_dir, "synth_nonneg.npz")))  # non-negative cases (round 2)
+    return both
 
 
-@pytest.mark.parametrize("name", datagen.CASE_NAMES)
+@pytest.mark.parametrize("name", datagen.CASE_NAMES + datagen.RELU_CASE_NAMES)
 def test_exact_topk_bitwise_vs_seq_oracle_and_golden(name, synth):
     c = datagen.make_case(name)
     sims, idx = b200knn.knn_topk(_t(c["feature"]), _t(c["bank"]), c["k"], mode="exact")
@@ -39,7 +41,7 @@ def test_exact_topk_bitwise_vs_seq_oracle_and_golden(name, synth):
     assert r["max_rel_err"] <= 1e-5  # north-star: similarities within 1e-5 relative of fp64
 
 
-@pytest.mark.parametrize("name", datagen.CASE_NAMES)
+@pytest.mark.parametrize("name", datagen.CASE_NAMES + datagen.RELU_CASE_NAMES)
 def test_knn_predict_vs_goldens(name, synth):
     c = datagen.make_case(name)
     b200knn.set_default_mode("exact")

@@ -13,10 +13,12 @@ from oracle import knn_oracle as O
 
 @pytest.fixture(scope="module")
 def synth(golden_dir):
-    return np.load(os.path.join(golden_dir, "synth.npz"))
+    both = dict(np.load(os.path.join(golden_dir, "synth.npz")))
+    both.update(np.load(os.path.join(golden_dir, "synth_nonneg.npz")))  # non-negative cases (round 2)
+    return both
 
 
-@pytest.mark.parametrize("name", datagen.CASE_NAMES)
+@pytest.mark.parametrize("name", datagen.CASE_NAMES + datagen.RELU_CASE_NAMES)
 def test_seq_and_o64_match_golden(name, synth):
     c = datagen.make_case(name)
     ss, si = O.topk_seqfma(c["feature"], c["bank"], c["k"])
@@ -28,7 +30,7 @@ def test_seq_and_o64_match_golden(name, synth):
     assert np.array_equal(p64, synth[name + "_o64_pred"].astype(np.int64))
 
 
-@pytest.mark.parametrize("name", datagen.CASE_NAMES)
+@pytest.mark.parametrize("name", datagen.CASE_NAMES + datagen.RELU_CASE_NAMES)
 def test_r32_matches_golden_under_contract(name, synth):
     """torch CPU fp32 (the reference algorithm verbatim) is not bitwise stable across thread
     counts / MKL versions, so it is pinned through the contract, not bitwise."""
