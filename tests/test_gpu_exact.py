@@ -36,7 +36,12 @@ def test_exact_topk_bitwise_vs_seq_oracle_and_golden(name, synth):
     assert np.array_equal(sims.view(np.uint32), ss.view(np.uint32))
     assert np.array_equal(idx, synth[name + "_seq_idx"].astype(np.int64))
     assert np.array_equal(sims.view(np.uint32), synth[name + "_seq_sims"].view(np.uint32))
-    r = O.compare_topk(sims, idx, c["feature"], c["bank"], c["k"])
+    # positions whose fp64 neighbours are closer than eps * max|s| are ambiguous in fp32.  Same-sign
+    # products (non-negative rows) do not cancel, so fp32 rounding of ANY summation order reaches
+    # 1.6e-6 relative there (measured: sequential fma vs fp64 on absgauss_small) against 6e-7 on
+    # sign-symmetric rows: the ambiguity window of those cases is 2e-6 instead of 4e-7
+    eps = 2e-6 if name in datagen.RELU_CASE_NAMES else 4e-7
+    r = O.compare_topk(sims, idx, c["feature"], c["bank"], c["k"], eps_scale=eps)
     assert r["idx_mismatch_unambiguous"] == 0 and r["set_mismatch_rows_unambiguous"] == 0
     assert r["max_rel_err"] <= 1e-5  # north-star: similarities within 1e-5 relative of fp64
 
