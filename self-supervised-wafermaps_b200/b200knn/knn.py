@@ -171,9 +171,10 @@ def set_default_mode(mode: str) -> None:
 
     ``"exact"``     fp32 CUDA-core contraction, sequential-fma similarities (bitwise reproducible);
     ``"fp32"``      tensor-core candidates + exact re-scoring + certificate, cascading fp16 (1 MMA per
-                    k-step, k+40 candidates) -> fp16 x split-fp16 (2 MMAs, k+40) -> split-BF16 (3 MMAs,
-                    k+16) -> 3xTF32 (k+8) -> exact for the rows each level cannot certify: bitwise the
-                    ``"exact"`` result at tensor-core speed (the fp32-matching mode);
+                    k-step, k + 40..160 candidates, the margin following how bunched the bank's
+                    similarities are) -> fp16 x split-fp16 (2 MMAs, k + 160) -> the same with the widest
+                    margin the lists allow (k_in = 992) -> exact, for the rows each level cannot certify:
+                    bitwise the ``"exact"`` result at tensor-core speed (the fp32-matching mode);
     ``"fp32_f16"`` / ``"fp32_f16x2"`` / ``"fp32_bf16x3"`` / ``"fp32_tf32"`` / ``"fp32_bf16"``  a single level
                     (then exact);
     ``"f16"``       raw tcgen05 fp16 similarities (2^-10 relative to ||q|| ||x||; BF16 mode's speed);
