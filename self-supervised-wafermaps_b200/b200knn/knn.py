@@ -52,7 +52,7 @@ class _Timed:
     def __init__(self, name: str, on: bool = True):
         self.name = name
         self.ev = None
-        if on and profile_events is not None:
+        if on and profile_events is not None and not torch.cuda.is_current_stream_capturing():
             self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
     def __enter__(self):
