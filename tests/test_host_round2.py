@@ -105,3 +105,15 @@ def test_bench_generators_cover_the_reference_distribution():
     a = bench.make_inputs(torch.device("cpu"), 3000, 50, 64, seed=1, kind="relu", row_range=(1000, 2000))[0]
     b = bench.make_inputs(torch.device("cpu"), 3000, 50, 64, seed=1, kind="relu")[0]
     assert torch.equal(a, b[1000:2000])  # shard-reproducible
+
+
+def test_bench_library_bar_is_the_reference_op_sequence():
+    """bench.py's `gpu_library_baseline` restates lightly's knn_predict inline (it may not import the
+    oracle for that leg): on CPU it must give exactly what the oracle's R32 gives."""
+    import bench
+    from oracle import knn_oracle as O
+
+    c = datagen.make_case("mixed38")
+    f, bank, lab = (torch.from_numpy(c[n]) for n in ("feature", "bank", "labels"))
+    got = bench.library_knn_predict(f, bank, lab, c["C"], c["k"], c["t"])
+    assert torch.equal(got, O.knn_predict_r32(f, bank, lab, c["C"], c["k"], c["t"]))
